@@ -1,0 +1,406 @@
+#!/usr/bin/env python
+"""bench.py — the measurement contract for the LZ4 block hot path on B200.
+
+One "step" = one pass of the hot path over one batch of independent 64 KiB blocks:
+fast-compress the whole batch, then fast-decompress it again (LZ4Factory.fastCompressor()
++ fastDecompressor(), BASELINE.json configs[1]).  `value` = uncompressed GiB processed per
+second by that round trip, inputs resident in HBM, timed with CUDA events on the launching
+stream, max over ranks.  Extra keys break the step into its compress and decompress halves,
+give the compression ratio next to the reference's, the HBM roofline of the dominant kernel,
+an end-to-end number through the C ABI with HOST buffers, and the reference's own CPU path
+timed on this box's host cores.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+                  [--blocks B]      # blocks per GPU (default 1048576 = BASELINE configs[1])
+
+Multi-GPU: one process per GPU (torchrun), contiguous block ranges per rank, no collective
+on the data path; only the timing is all-reduced (max) over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BLOCK = 65536
+METRIC = "lz4_fast_compress_plus_decompress_64KiB_blocks"
+UNIT = "GiB/s"
+GIB = float(1 << 30)
+
+
+def env_int(name, default):
+    return int(os.environ.get(name, default))
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ corpus
+def host_corpus(chk, nblocks: int, seed: int = 2):
+    """The reference's own synthetic generator (`lz4 -b` default: RDG_genBuffer P=0.50), cut at 64 KiB."""
+    return chk.datagen(nblocks * BLOCK, 0.5, 0.0, seed)
+
+
+def cpu_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_roundtrip(chk, data, nblocks, threads, passes=3):
+    """compress + fast-decompress `nblocks` blocks on `threads` host threads with the CPU library.
+    Returns dict with GiB/s for each half, the round trip, and the ratio."""
+    import numpy as np
+    from oracle import oracle as O
+    bound = chk.compress_bound(BLOCK)
+    stride = (bound + 15) // 16 * 16
+    soff = np.arange(nblocks, dtype=np.uint64) * np.uint64(BLOCK)
+    slen = np.full(nblocks, BLOCK, dtype=np.int32)
+    coff = np.arange(nblocks, dtype=np.uint64) * np.uint64(stride)
+    ccap = np.full(nblocks, bound, dtype=np.int32)
+    comp = np.empty(nblocks * stride, dtype=np.uint8)
+    out = np.empty(nblocks * BLOCK, dtype=np.uint8)
+    tc, tcm, clen = O.cpu_bench(chk, "compress", data, soff, slen, comp, coff, ccap, threads, passes)
+    td, tdm, dres = O.cpu_bench(chk, "dec_fast", comp, coff, ccap, out, soff, slen, threads, passes)
+    assert (dres == clen).all() and (out == data[: nblocks * BLOCK]).all(), "CPU round trip mismatch"
+    nbytes = nblocks * BLOCK
+    return {"compress_gibs": nbytes / tc / GIB, "decompress_gibs": nbytes / td / GIB,
+            "roundtrip_gibs": nbytes / (tc + td) / GIB, "ratio": nbytes / float(clen.sum()),
+            "t_compress_s": tc, "t_decompress_s": td}
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def run_reference(args):
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return 0
+    from oracle import oracle as O
+    chk = O.best_available()
+    threads = cpu_threads()
+    nblocks = args.ref_blocks
+    data = host_corpus(chk, nblocks)
+    # W warm-up + K timed steps; each step = one bounded-sample round trip (best of 1 pass inside)
+    for _ in range(args.warmup):
+        cpu_roundtrip(chk, data, nblocks, threads, passes=1)
+    t0 = time.perf_counter()
+    rs = [cpu_roundtrip(chk, data, nblocks, threads, passes=1) for _ in range(args.steps)]
+    wall = time.perf_counter() - t0
+    tsum = sum(r["t_compress_s"] + r["t_decompress_s"] for r in rs)
+    nbytes = nblocks * BLOCK
+    value = nbytes * args.steps / tsum / GIB
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * tsum / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": {"workload": f"{nblocks} x 64 KiB blocks (bounded sample of configs[1]), RDG_genBuffer P=0.50 seed=2, "
+                               "LZ4_compress_default + LZ4_decompress_fast on host cores", "threads": threads},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": chk.kind,
+                         "sample": f"{nblocks} blocks = {nbytes / GIB:.1f} GiB per step, {args.steps} steps",
+                         "compress_gibs": sum(r["compress_gibs"] for r in rs) / len(rs),
+                         "decompress_gibs": sum(r["decompress_gibs"] for r in rs) / len(rs),
+                         "ratio": rs[0]["ratio"]},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": wall,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------ B200 arm
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+
+    import lz4java_b200 as L
+    from oracle import oracle as O
+    lib = L._native.lib()
+    L._native.check(lib.b200lz4_set_device(local))
+    ctypes.c_int.in_dll(lib, "b200lz4_compress_hash_log").value = args.hash_log
+    B = L.batch
+
+    nblk = args.blocks                       # per GPU (weak scaling: every rank gets the same range size)
+    nbytes = nblk * BLOCK
+    bound = L.max_compressed_length(BLOCK)
+    stride = (bound + 15) // 16 * 16        # 65 824: 16-byte aligned compressed slots
+
+    # ---- corpus: 1 GiB of RDG P=0.50 (seed 2 + rank) on the host, uploaded once, tiled across HBM with a
+    # per-block perturbation of the first 8 bytes so blocks are distinct (ratio unchanged)
+    chk = O.best_available()
+    base_blocks = min(nblk, 16384)
+    host = host_corpus(chk, base_blocks, seed=2 + rank)
+    base = torch.from_numpy(host).to(dev)
+    src = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    reps = (nblk + base_blocks - 1) // base_blocks
+    for r in range(reps):
+        lo = r * base_blocks * BLOCK
+        hi = min(nbytes, lo + base_blocks * BLOCK)
+        src[lo:hi] = base[: hi - lo]
+    idx = torch.arange(nblk, device=dev, dtype=torch.int64) + rank * nblk
+    v = src.view(nblk, BLOCK)
+    for k in range(8):
+        v[:, k] ^= ((idx >> (8 * k)) & 0xFF).to(torch.uint8)
+    del base, idx
+
+    soff = torch.arange(nblk, device=dev, dtype=torch.int64) * BLOCK
+    slen = torch.full((nblk,), BLOCK, device=dev, dtype=torch.int32)
+    coff = torch.arange(nblk, device=dev, dtype=torch.int64) * stride
+    ccap = torch.full((nblk,), bound, device=dev, dtype=torch.int32)
+    comp = torch.empty(nblk * stride, dtype=torch.uint8, device=dev)
+    clen = torch.zeros(nblk, device=dev, dtype=torch.int32)
+    dres = torch.zeros(nblk, device=dev, dtype=torch.int32)
+    h_before = torch.zeros(nblk, device=dev, dtype=torch.int64)
+    h_after = torch.zeros(nblk, device=dev, dtype=torch.int64)
+    B.xxh64_batch_dev(src, soff, slen, h_before, 0)        # checksum of every original block
+
+    # decompression writes back into the source range: a correct round trip leaves it bit-identical,
+    # which the checksum-of-checksums below proves; a third 64 GiB buffer would not fit next to
+    # src + compressed slots in 180 GB.
+    def step(ev=None):
+        B.compress_fast_batch_dev(src, soff, slen, comp, coff, ccap, clen, BLOCK)
+        if ev is not None:
+            ev.record()
+        B.decompress_fast_batch_dev(comp, coff, ccap, src, soff, slen, dres)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    lib.b200lz4_launch_count_reset()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    mids = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    e0.record()
+    for k in range(args.steps):
+        starts[k].record()
+        step(mids[k])
+    e1.record()
+    barrier()
+    launches = int(lib.b200lz4_launch_count())
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = e0.elapsed_time(e1)
+    t_comp_ms = sum(starts[k].elapsed_time(mids[k]) for k in range(args.steps)) / args.steps
+    t_step_ms = total_ms / args.steps
+    t_dec_ms = t_step_ms - t_comp_ms
+
+    # ---- correctness of what was timed (outside the timed region)
+    csum = int(clen.sum().item())
+    ok = bool((clen > 0).all().item()) and bool((dres == clen).all().item())
+    B.xxh64_batch_dev(src, soff, slen, h_after, 0)
+    ok = ok and bool(torch.equal(h_before, h_after))
+    if not ok:
+        raise SystemExit("bench: GPU round trip is not bit-exact — number invalid")
+    # a sample of compressed blocks must decode with the CPU checker too
+    for b in (0, nblk // 2, nblk - 1):
+        c = comp[b * stride: b * stride + int(clen[b].item())].cpu().numpy()
+        r, o = chk.decompress_safe(c, BLOCK)
+        if r != BLOCK or o != src[b * BLOCK:(b + 1) * BLOCK].cpu().numpy().tobytes():
+            raise SystemExit("bench: CPU checker rejects a GPU-compressed block")
+
+    # ---- max over ranks (device time)
+    tt = torch.tensor([t_step_ms, t_comp_ms, t_dec_ms], device=dev, dtype=torch.float64)
+    cs = torch.tensor([float(csum)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cs, op=dist.ReduceOp.SUM)
+    t_step_ms, t_comp_ms, t_dec_ms = (float(x) for x in tt.tolist())
+    total_bytes = nbytes * world
+    total_comp = float(cs.item())
+    value = total_bytes / (t_step_ms / 1e3) / GIB
+
+    # ---- end to end through the C ABI with HOST (pinned) buffers: H2D + kernels + D2H inside the timed region
+    e2e = run_e2e(args, L, dev, host, rank, world)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
+        algo_bytes = nbytes + csum                                  # N + C per compress launch (this rank)
+        achieved = algo_bytes / (t_comp_ms / 1e3) / 1e9
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "compress_traffic.json")))
+            if tj.get("blocks") == nblk and tj.get("hash_log") == args.hash_log:
+                traffic = tj["dram_bytes_per_launch"]
+        except Exception:
+            pass
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            threads = cpu_threads()
+            n_cpu = args.cpu_blocks
+            cdata = host if base_blocks >= n_cpu else host_corpus(chk, n_cpu, seed=2)
+            r = cpu_roundtrip(chk, cdata, n_cpu, threads, passes=3)
+            cpu = {"value": r["roundtrip_gibs"], "unit": UNIT, "cores": threads, "kind": chk.kind,
+                   "sample": f"{n_cpu} blocks = {n_cpu * BLOCK / GIB:.2f} GiB of the same corpus, best of 3 passes, "
+                             f"{threads} pthreads, LZ4_compress_default + LZ4_decompress_fast",
+                   "compress_gibs": r["compress_gibs"], "decompress_gibs": r["decompress_gibs"], "ratio": r["ratio"]}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": t_step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8", "data": "synthetic",
+            "config": {"workload": f"{nblk} x 64 KiB independent blocks per GPU (BASELINE configs[1]), "
+                                   "fast compress + fast decompress, RDG_genBuffer P=0.50 tiled from 1 GiB",
+                       "blocks_per_gpu": nblk, "block_bytes": BLOCK, "hash_log": args.hash_log,
+                       "l2": "inputs (64 GiB per GPU) larger than L2; no flush needed", "parallelism": f"range-shard x{world}"},
+            "compress_gibs": total_bytes / (t_comp_ms / 1e3) / GIB,
+            "decompress_gibs": total_bytes / (t_dec_ms / 1e3) / GIB,
+            "ratio": total_bytes / total_comp,
+            "roofline": {"bound": "hbm", "kernel": "lz4_compress_fast_kernel", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "frac_of_nominal_8TBs": achieved / 8000.0,
+                         "traffic": traffic, "algorithmic_bytes_per_launch": algo_bytes, "peak_source": peak_src,
+                         "decompress_achieved": algo_bytes / (t_dec_ms / 1e3) / 1e9},
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "verified": "xxh64 of every block before == after all steps; 3 blocks re-decoded by the CPU checker",
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def run_e2e(args, L, dev, host, rank, world):
+    """Same step through the public C-ABI batch calls with pinned HOST buffers (what a JNI caller
+    with DirectByteBuffers does): compress_fast_compact_host then decompress_fast_batch_host."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    B = L.batch
+    n = min(args.e2e_blocks, args.blocks)
+    nbytes = n * BLOCK
+    bound = L.max_compressed_length(BLOCK)
+    src_t = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    comp_t = torch.empty(n * bound, dtype=torch.uint8).pin_memory()
+    out_t = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    src, comp, out = src_t.numpy(), comp_t.numpy(), out_t.numpy()
+    reps = (nbytes + len(host) - 1) // len(host)
+    for r in range(reps):
+        lo = r * len(host); hi = min(nbytes, lo + len(host))
+        src[lo:hi] = host[: hi - lo]
+    soff, slen = B.uniform_layout(n, BLOCK)
+
+    def step():
+        ooff, olen, total = B.compress_fast_compact_host(src, soff, slen, comp, BLOCK)
+        res = B.decompress_fast_batch_host(comp, ooff, olen, out, soff, slen)
+        return ooff, olen, total, res
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ooff, olen, total, res = step()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    assert (res == olen).all() and (out == src).all(), "e2e round trip mismatch"
+    t = torch.tensor([dt], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item())
+    per_step_h2d = nbytes + total + 2 * n * 28          # payload both ways + descriptors
+    per_step_d2h = total + nbytes + 2 * n * 28
+    return {"value": nbytes * world * args.steps / dt / GIB, "unit": UNIT,
+            "h2d_bytes_per_step": int(per_step_h2d), "d2h_bytes_per_step": int(per_step_d2h),
+            "sample": f"{n} blocks per GPU per step through b200lz4_compress_fast_compact_host + "
+                      "b200lz4_decompress_fast_batch_host, pinned host buffers, wall clock (max over ranks)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--blocks", type=int, default=1 << 20, help="blocks per GPU")
+    ap.add_argument("--e2e-blocks", type=int, default=1 << 16, help="blocks per GPU per e2e step (4 GiB)")
+    ap.add_argument("--cpu-blocks", type=int, default=1 << 14, help="blocks in the cpu_baseline sample (1 GiB)")
+    ap.add_argument("--ref-blocks", type=int, default=1 << 15, help="blocks per step for --impl reference (2 GiB)")
+    ap.add_argument("--hash-log", type=int, default=13)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,152 @@
+/*
+ * b200lz4.h — C ABI of libb200lz4.so, the B200 (sm_100a) LZ4 block codec + XXHash backend.
+ *
+ * This is the drop-in boundary for the one hot path of lz4-java: the functions below are
+ * what a `net.jpountz.lz4.LZ4B200JNI` / `net.jpountz.xxhash.XXHashB200JNI` shim binds, in
+ * the same way the reference's JNI shim binds the vendored C:
+ *
+ *   reference call site (under /root/reference)                       replaced by
+ *   src/jni/net_jpountz_lz4_LZ4JNI.c:75   LZ4_compress_default        b200lz4_compress_default
+ *   src/jni/net_jpountz_lz4_LZ4JNI.c:122  LZ4_compress_HC             b200lz4_compress_HC
+ *   src/jni/net_jpountz_lz4_LZ4JNI.c:169  LZ4_decompress_fast         b200lz4_decompress_fast
+ *   src/jni/net_jpountz_lz4_LZ4JNI.c:216  LZ4_decompress_safe         b200lz4_decompress_safe
+ *   src/jni/net_jpountz_lz4_LZ4JNI.c:237  LZ4_compressBound           b200lz4_compressBound
+ *   src/jni/net_jpountz_xxhash_XXHashJNI.c:54,78    XXH32             b200xxh32
+ *   src/jni/net_jpountz_xxhash_XXHashJNI.c:164,188  XXH64             b200xxh64
+ *   src/jni/net_jpountz_xxhash_XXHashJNI.c:89-145   XXH32_* state     b200xxh32_create/reset/update/digest/free
+ *   src/jni/net_jpountz_xxhash_XXHashJNI.c:199-255  XXH64_* state     b200xxh64_create/reset/update/digest/free
+ *
+ * All arithmetic runs in hand-written CUDA kernels; there is NO CPU fallback: every entry
+ * point returns B200LZ4_E_NODEVICE (or 0 for the hash one-shots, with b200lz4_last_error()
+ * set) when no sm_100 device/driver is usable.
+ *
+ * Return conventions are the reference's:
+ *   compress          > 0 compressed size, 0 if dst is too small / input too large
+ *   decompress_safe   >= 0 decoded size, < 0 == -(error position)-1   (lz4.c:2337)
+ *   decompress_fast   >= 0 compressed bytes consumed, -1 on any error  (lz4.c:1890)
+ *
+ * Besides the one-block-per-call functions (what the net.jpountz API needs, n = 1), the
+ * library exposes BATCH calls: one launch over n independent blocks.  These are the calls
+ * that make a GPU backend meaningful (SURVEY.md §7 "hard parts" 1); the single-block calls
+ * are the n = 1 case of the host batch path.
+ */
+#ifndef B200LZ4_H
+#define B200LZ4_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200LZ4_VERSION        100          /* 0.1.0 */
+#define B200LZ4_E_NODEVICE     (-1000001)   /* no usable CUDA device / driver            */
+#define B200LZ4_E_CUDA         (-1000002)   /* CUDA runtime error, see b200lz4_last_error */
+#define B200LZ4_E_ARG          (-1000003)   /* invalid argument                           */
+
+/* ---------------------------------------------------------------- library / device */
+int         b200lz4_version(void);
+int         b200lz4_device_count(void);           /* >= 0, or B200LZ4_E_NODEVICE            */
+int         b200lz4_set_device(int device);       /* device used by the calling thread      */
+const char* b200lz4_last_error(void);             /* thread-local, never NULL                */
+/* Pin / unpin a caller-owned host range (e.g. a Java DirectByteBuffer) so the host batch
+ * calls DMA straight from/to it.  Optional: unpinned memory works, slower. */
+int         b200lz4_host_register(void* p, size_t bytes);
+int         b200lz4_host_unregister(void* p);
+
+/* ---------------------------------------------------------------- one block per call, HOST buffers */
+int b200lz4_compressBound(int inputSize);                                            /* lz4.h:212 */
+int b200lz4_compress_default(const char* src, char* dst, int srcSize, int dstCapacity);
+int b200lz4_compress_HC(const char* src, char* dst, int srcSize, int dstCapacity, int level);
+int b200lz4_decompress_safe(const char* src, char* dst, int compressedSize, int dstCapacity);
+/* LZ4_decompress_fast does not know the input size (lz4.c:1788); a device copy needs one.
+ * `srcAvail` is the number of readable bytes at src (the Java wrapper knows it:
+ * src.length - srcOff).  b200lz4_decompress_fast() assumes compressBound(originalSize). */
+int b200lz4_decompress_fast_bounded(const char* src, int srcAvail, char* dst, int originalSize);
+int b200lz4_decompress_fast(const char* src, char* dst, int originalSize);
+
+uint32_t b200xxh32(const void* input, size_t len, uint32_t seed);
+uint64_t b200xxh64(const void* input, size_t len, uint64_t seed);
+
+/* streaming hash state: opaque handle (jlong on the Java side) */
+void*    b200xxh32_create(uint32_t seed);
+void     b200xxh32_reset(void* state, uint32_t seed);
+int      b200xxh32_update(void* state, const void* input, size_t len);
+uint32_t b200xxh32_digest(void* state);
+void     b200xxh32_free(void* state);
+void*    b200xxh64_create(uint64_t seed);
+void     b200xxh64_reset(void* state, uint64_t seed);
+int      b200xxh64_update(void* state, const void* input, size_t len);
+uint64_t b200xxh64_digest(void* state);
+void     b200xxh64_free(void* state);
+
+/* ---------------------------------------------------------------- batches, DEVICE-resident
+ * Every pointer is a device pointer on the current device; `stream` is a cudaStream_t
+ * (NULL = default stream).  Block i reads  src_base + src_off[i]  (src_len[i] bytes) and
+ * writes dst_base + dst_off[i] (at most dst_cap[i] bytes); result[i] follows the
+ * single-block return convention.  The calls are asynchronous on `stream` and return 0 or
+ * a B200LZ4_E_* code for launch failures.
+ *
+ * compress_fast: `max_src_len` is an upper bound on src_len[] chosen by the caller
+ * (<= 65536 selects the 16-bit position table like lz4.c:1353; 0 = unknown -> 32-bit). */
+int b200lz4_compress_fast_batch_dev(const uint8_t* src_base, const uint64_t* src_off, const int32_t* src_len,
+                                    uint8_t* dst_base, const uint64_t* dst_off, const int32_t* dst_cap,
+                                    int32_t* result, size_t n, int max_src_len, void* stream);
+int b200lz4_compress_hc_batch_dev(const uint8_t* src_base, const uint64_t* src_off, const int32_t* src_len,
+                                  uint8_t* dst_base, const uint64_t* dst_off, const int32_t* dst_cap,
+                                  int32_t* result, size_t n, int level, void* stream);
+int b200lz4_decompress_safe_batch_dev(const uint8_t* src_base, const uint64_t* src_off, const int32_t* src_len,
+                                      uint8_t* dst_base, const uint64_t* dst_off, const int32_t* dst_cap,
+                                      int32_t* result, size_t n, void* stream);
+/* decompress_fast: src_avail[i] = readable bytes at the block's src; dst_len[i] = exact original size */
+int b200lz4_decompress_fast_batch_dev(const uint8_t* src_base, const uint64_t* src_off, const int32_t* src_avail,
+                                      uint8_t* dst_base, const uint64_t* dst_off, const int32_t* dst_len,
+                                      int32_t* result, size_t n, void* stream);
+/* hashes: len[] may be anything >= 0; one seed for the batch (the Java API passes one seed per call) */
+int b200xxh32_batch_dev(const uint8_t* base, const uint64_t* off, const int32_t* len,
+                        uint32_t seed, uint32_t* out, size_t n, void* stream);
+int b200xxh64_batch_dev(const uint8_t* base, const uint64_t* off, const int32_t* len,
+                        uint64_t seed, uint64_t* out, size_t n, void* stream);
+
+/* ---------------------------------------------------------------- batches, HOST buffers
+ * Same contracts, but every pointer is a HOST pointer.  The library chunks the batch and
+ * pipelines H2D copy / kernel / D2H copy on several streams of the current device.  Blocks
+ * must be laid out in ascending, non-overlapping order in both src and dst (the natural
+ * layout of a block list over a DirectByteBuffer).  Synchronous: returns when all results
+ * and output bytes are in host memory.  Returns 0 or a B200LZ4_E_* code. */
+int b200lz4_compress_fast_batch_host(const uint8_t* src_base, const uint64_t* src_off, const int32_t* src_len,
+                                     uint8_t* dst_base, const uint64_t* dst_off, const int32_t* dst_cap,
+                                     int32_t* result, size_t n, int max_src_len);
+int b200lz4_compress_hc_batch_host(const uint8_t* src_base, const uint64_t* src_off, const int32_t* src_len,
+                                   uint8_t* dst_base, const uint64_t* dst_off, const int32_t* dst_cap,
+                                   int32_t* result, size_t n, int level);
+int b200lz4_decompress_safe_batch_host(const uint8_t* src_base, const uint64_t* src_off, const int32_t* src_len,
+                                       uint8_t* dst_base, const uint64_t* dst_off, const int32_t* dst_cap,
+                                       int32_t* result, size_t n);
+int b200lz4_decompress_fast_batch_host(const uint8_t* src_base, const uint64_t* src_off, const int32_t* src_avail,
+                                       uint8_t* dst_base, const uint64_t* dst_off, const int32_t* dst_len,
+                                       int32_t* result, size_t n);
+int b200xxh32_batch_host(const uint8_t* base, const uint64_t* off, const int32_t* len,
+                         uint32_t seed, uint32_t* out, size_t n);
+int b200xxh64_batch_host(const uint8_t* base, const uint64_t* off, const int32_t* len,
+                         uint64_t seed, uint64_t* out, size_t n);
+
+/* Compact-output compress for pipelines that want one contiguous stream (e.g. a frame
+ * writer): blocks are compressed and written back-to-back into dst_base; out_off[i] and
+ * result[i] give each block's position and size; *total = bytes written.  dst_capacity
+ * must be >= sum(compressBound(src_len[i])) only in the worst case; the call fails with
+ * B200LZ4_E_ARG if the compacted stream does not fit. */
+int b200lz4_compress_fast_compact_host(const uint8_t* src_base, const uint64_t* src_off, const int32_t* src_len,
+                                       uint8_t* dst_base, size_t dst_capacity, uint64_t* out_off,
+                                       int32_t* result, size_t n, int max_src_len, uint64_t* total);
+
+/* kernel-launch counter (bench.py's "gpu_launches"): number of kernels this library has
+ * launched from the calling process since load / since the last reset. */
+uint64_t b200lz4_launch_count(void);
+void     b200lz4_launch_count_reset(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200LZ4_H */

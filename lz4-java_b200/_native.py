@@ -1,0 +1,88 @@
+"""ctypes loader for libb200lz4.so (include/b200lz4.h).  No fallback: if the CUDA library is
+missing or no B200 is usable, callers get an exception, never a CPU path."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(_HERE, "libb200lz4.so")
+
+E_NODEVICE, E_CUDA, E_ARG = -1000001, -1000002, -1000003
+
+# every symbol include/b200lz4.h declares: (name, restype, argtypes)
+_vp, _i, _sz, _u32, _u64, _i32 = C.c_void_p, C.c_int, C.c_size_t, C.c_uint32, C.c_uint64, C.c_int32
+_BATCH = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz]
+SYMBOLS = [
+    ("b200lz4_version", _i, []),
+    ("b200lz4_device_count", _i, []),
+    ("b200lz4_set_device", _i, [_i]),
+    ("b200lz4_last_error", C.c_char_p, []),
+    ("b200lz4_host_register", _i, [_vp, _sz]),
+    ("b200lz4_host_unregister", _i, [_vp]),
+    ("b200lz4_compressBound", _i, [_i]),
+    ("b200lz4_compress_default", _i, [_vp, _vp, _i, _i]),
+    ("b200lz4_compress_HC", _i, [_vp, _vp, _i, _i, _i]),
+    ("b200lz4_decompress_safe", _i, [_vp, _vp, _i, _i]),
+    ("b200lz4_decompress_fast_bounded", _i, [_vp, _i, _vp, _i]),
+    ("b200lz4_decompress_fast", _i, [_vp, _vp, _i]),
+    ("b200xxh32", _u32, [_vp, _sz, _u32]),
+    ("b200xxh64", _u64, [_vp, _sz, _u64]),
+    ("b200xxh32_create", _vp, [_u32]),
+    ("b200xxh32_reset", None, [_vp, _u32]),
+    ("b200xxh32_update", _i, [_vp, _vp, _sz]),
+    ("b200xxh32_digest", _u32, [_vp]),
+    ("b200xxh32_free", None, [_vp]),
+    ("b200xxh64_create", _vp, [_u64]),
+    ("b200xxh64_reset", None, [_vp, _u64]),
+    ("b200xxh64_update", _i, [_vp, _vp, _sz]),
+    ("b200xxh64_digest", _u64, [_vp]),
+    ("b200xxh64_free", None, [_vp]),
+    ("b200lz4_compress_fast_batch_dev", _i, _BATCH + [_i, _vp]),
+    ("b200lz4_compress_hc_batch_dev", _i, _BATCH + [_i, _vp]),
+    ("b200lz4_decompress_safe_batch_dev", _i, _BATCH + [_vp]),
+    ("b200lz4_decompress_fast_batch_dev", _i, _BATCH + [_vp]),
+    ("b200xxh32_batch_dev", _i, [_vp, _vp, _vp, _u32, _vp, _sz, _vp]),
+    ("b200xxh64_batch_dev", _i, [_vp, _vp, _vp, _u64, _vp, _sz, _vp]),
+    ("b200lz4_compress_fast_batch_host", _i, _BATCH + [_i]),
+    ("b200lz4_compress_hc_batch_host", _i, _BATCH + [_i]),
+    ("b200lz4_decompress_safe_batch_host", _i, _BATCH),
+    ("b200lz4_decompress_fast_batch_host", _i, _BATCH),
+    ("b200xxh32_batch_host", _i, [_vp, _vp, _vp, _u32, _vp, _sz]),
+    ("b200xxh64_batch_host", _i, [_vp, _vp, _vp, _u64, _vp, _sz]),
+    ("b200lz4_compress_fast_compact_host", _i, [_vp, _vp, _vp, _vp, _sz, _vp, _vp, _sz, _i, _vp]),
+    ("b200lz4_launch_count", _u64, []),
+    ("b200lz4_launch_count_reset", None, []),
+]
+
+_lib = None
+
+
+class B200Error(RuntimeError):
+    """The CUDA backend failed (no device, CUDA error, bad batch layout).  Never swallowed."""
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(SO_PATH):
+            raise ImportError(
+                f"{SO_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(make -C lz4-java_b200/csrc).  There is no CPU fallback.")
+        L = C.CDLL(SO_PATH)
+        for name, res, args in SYMBOLS:
+            f = getattr(L, name)          # AttributeError here == ABI/header mismatch
+            f.restype = res
+            f.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc: int) -> int:
+    if rc in (E_NODEVICE, E_CUDA, E_ARG):
+        raise B200Error(f"libb200lz4: {lib().b200lz4_last_error().decode()} (code {rc})")
+    return rc
+
+
+def last_error() -> str:
+    return lib().b200lz4_last_error().decode()

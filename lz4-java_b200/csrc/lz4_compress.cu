@@ -1,0 +1,258 @@
+// lz4_compress.cu — batch LZ4 fast block compression, one independent block per warp.
+//
+// Replaces the reference's LZ4_compress_default (lz4.c:1435 -> 1416 -> 1346 -> 910-1302) as
+// called from the JNI shim (src/jni/net_jpountz_lz4_LZ4JNI.c:75).  Same algorithm family — greedy
+// single-probe LZ77 over a 4-byte multiplicative hash (lz4.c:756-762), 16-bit block-relative
+// position table for blocks < 64 KiB (lz4.c:1353), MFLIMIT/LASTLITERALS end rules (lz4.c:243-244)
+// — but re-shaped for a 32-lane warp, so the emitted stream is a *different valid parse* of the
+// same format (like the reference's own Java ports, README.md:45-47): it round-trips bit-exactly
+// through every LZ4 decoder; its ratio is reported next to the reference's.
+//
+// Warp algorithm (one "step" = 32 consecutive positions):
+//   1. lane l reads the 4 bytes at ip+l, hashes them, fetches the candidate position from the
+//      warp's private hash table in shared memory;
+//   2. candidates are verified against the block (4-byte compare); __ballot_sync + __ffs picks the
+//      FIRST matching position (greedy, like the scalar parse);
+//   3. lanes at or before the match start publish their positions to the table (positions after
+//      the match start are not published: they will be probed again after the match);
+//   4. the match is extended backwards (catch-up, lz4.c:1080) and forwards (LZ4_count,
+//      lz4.c:659-682) with lane-parallel compares + ballot;
+//   5. token / literal run / offset / length bytes are emitted with lane-parallel stores.
+// Without a hit the step costs one pass and advances 32 positions.
+//
+// Algorithmic HBM bytes per block: N (input read once) + C (output written once).  The table
+// (2^HASH_LOG entries) lives in shared memory and never touches HBM.
+#include "common.cuh"
+#include "kernels.h"
+#include <type_traits>
+
+namespace b200 {
+
+// ---- input accessors: the block either stays in global memory (L1/L2-cached) or is staged whole
+// into shared memory by a TMA bulk copy (blocks <= 64 KiB); the parser is written once over both.
+struct InGlobal {
+    const uint8_t* __restrict__ p;
+    __device__ __forceinline__ uint32_t ld1(int i) const { return p[i]; }
+    __device__ __forceinline__ uint32_t ld4(int i) const { return load_u32_unaligned(p + i); }
+    __device__ __forceinline__ const uint8_t* ptr(int i) const { return p + i; }
+};
+struct InShared {
+    const uint8_t* p;     // generic pointer into the CTA's shared memory
+    __device__ __forceinline__ uint32_t ld1(int i) const { return p[i]; }
+    __device__ __forceinline__ uint32_t ld4(int i) const {
+        const uint32_t a = (uint32_t)__cvta_generic_to_shared(p) + (uint32_t)i;
+        uint32_t lo, hi;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(lo) : "r"(a & ~3u));
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(hi) : "r"((a & ~3u) + 4u));
+        return __funnelshift_r(lo, hi, (a & 3u) * 8u);
+    }
+    __device__ __forceinline__ const uint8_t* ptr(int i) const { return p + i; }
+};
+
+// equal bytes between in[a..] and in[b..] (b < a), at most maxlen; 4 bytes per lane, 128 per round
+template <class In>
+__device__ __forceinline__ int match_extend(const In& in, int a, int b, int maxlen, int lane)
+{
+    int total = 0;
+    for (;;) {
+        const int i = total + lane * 4;
+        uint32_t x = 1;                                   // "differs at byte 0" beyond the limit
+        if (i < maxlen) x = in.ld4(a + i) ^ in.ld4(b + i);
+        const unsigned neq = __ballot_sync(B200_FULL, x != 0);
+        if (neq) {
+            const int fl = __ffs(neq) - 1;
+            const uint32_t xf = __shfl_sync(B200_FULL, x, fl);
+            const int pos = total + fl * 4 + ((__ffs(xf) - 1) >> 3);
+            return min(pos, maxlen);
+        }
+        total += 128;
+    }
+}
+
+// 255-chain for a length field whose token nibble saturated: v = length - 15 >= 0, cnt = v/255 + 1 bytes
+__device__ __forceinline__ void write_len_ext(uint8_t* d, int v, int cnt, int lane)
+{
+    for (int i = lane; i < cnt; i += 32) d[i] = (i == cnt - 1) ? uint8_t(v - 255 * (cnt - 1)) : uint8_t(255);
+}
+
+// The greedy warp parser.  Returns the compressed size, 0 if dst is too small.
+template <int HASH_LOG, bool U16, class In, class Entry>
+__device__ __forceinline__ int compress_block(const In in, const uint8_t* __restrict__ gsrc, int n,
+                                              uint8_t* __restrict__ dst, int cap, Entry* table, int lane)
+{
+    int op = 0, anchor = 0, ip = 0;
+    const int mflimit = n - 12;        // last position a match may start at (MFLIMIT, lz4.c:243)
+    const int matchlimit = n - 5;      // matches end here at the latest (LASTLITERALS, lz4.c:244)
+    int pf = 0;                        // software prefetch cursor (global input only)
+
+    while (ip <= mflimit) {            // n < 13 never finds a match: all literals (lz4.c:981)
+        if (std::is_same<In, InGlobal>::value) {
+            if (pf < ip + 2048) {      // keep ~4 KiB of the forward stream on its way to L2
+                const int q = pf + lane * 128;
+                if (q < n) asm volatile("prefetch.global.L2 [%0];" :: "l"(__cvta_generic_to_global(gsrc + q)));
+                pf += 4096;
+            }
+            if (lane < 2 && ip + 128 + lane * 128 < n)     // and the next two lines in L1
+                asm volatile("prefetch.global.L1 [%0];" :: "l"(__cvta_generic_to_global(gsrc + ip + 128 + lane * 128)));
+        }
+        const int p = ip + lane;
+        const bool valid = p <= mflimit;
+        uint32_t h = 0; int cand = 0; bool hit = false;
+        if (valid) {
+            const uint32_t seq = in.ld4(p);
+            h = (seq * 2654435761u) >> (32 - HASH_LOG);
+            cand = table[h];
+            if (cand < p && (U16 || p - cand <= 65535)) hit = in.ld4(cand) == seq;
+        }
+        const unsigned m = __ballot_sync(B200_FULL, hit);
+        const int f = m ? __ffs(m) - 1 : 31;
+        if (valid && lane <= f) table[h] = Entry(p);
+        if (m == 0) { ip += 32; continue; }
+
+        int ms = ip + f;                                        // match start
+        int mc = __shfl_sync(B200_FULL, cand, f);               // where the same bytes occurred before
+        int ml;
+        {   // one cooperative round for both directions: lane j compares offset d = j-8, i.e. up to
+            // 8 bytes of catch-up behind the match (lz4.c:1080) and its first 24 bytes (lz4.c:1153)
+            const int d = lane - 8;
+            const int backroom = min(ms - anchor, mc);
+            const bool ok = d < 0 ? (-d <= backroom) : (ms + d < matchlimit);
+            const bool eq = ok && in.ld1(ms + d) == in.ld1(mc + d);
+            const unsigned e = __ballot_sync(B200_FULL, eq);
+            const int back = __clz((~e) & 0xFFu) - 24;                       // ones below bit 8, contiguous from bit 7
+            const int fwd = __ffs((~(e >> 8)) | (1u << 24)) - 1;             // ones from bit 8 upwards, <= 24
+            ml = fwd;
+            if (fwd == 24) ml += match_extend(in, ms + 24, mc + 24, matchlimit - (ms + 24), lane);
+            ms -= back; mc -= back; ml += back;
+        }
+
+        // ---- emit one sequence: token, [literal length], literals, offset, [match length]
+        const int lit = ms - anchor;
+        const int mcode = ml - 4;
+        const int lhdr = lit >= 15 ? (lit - 15) / 255 + 1 : 0;
+        const int mhdr = mcode >= 15 ? (mcode - 15) / 255 + 1 : 0;
+        if ((long long)op + 1 + lhdr + lit + 2 + mhdr > cap) return 0;           // lz4.c:1085-1088, 1158
+        if (lane == 0) dst[op] = uint8_t((min(lit, 15) << 4) | min(mcode, 15));
+        op += 1;
+        if (lhdr) { write_len_ext(dst + op, lit - 15, lhdr, lane); op += lhdr; }
+        warp_copy(dst + op, in.ptr(anchor), lit, lane);
+        op += lit;
+        if (lane < 2) dst[op + lane] = uint8_t((ms - mc) >> (8 * lane));          // LE16 offset (lz4.c:1133)
+        op += 2;
+        if (mhdr) { write_len_ext(dst + op, mcode - 15, mhdr, lane); op += mhdr; }
+
+        ip = anchor = ms + ml;
+    }
+
+    {   // last literals (lz4.c:1266-1293)
+        const int lit = n - anchor;
+        const int lhdr = lit >= 15 ? (lit - 15) / 255 + 1 : 0;
+        if ((long long)op + 1 + lhdr + lit > cap) return 0;
+        if (lane == 0) dst[op] = uint8_t(min(lit, 15) << 4);
+        op += 1;
+        if (lhdr) { write_len_ext(dst + op, lit - 15, lhdr, lane); op += lhdr; }
+        warp_copy(dst + op, in.ptr(anchor), lit, lane);
+        op += lit;
+    }
+    return op;
+}
+
+static constexpr int STAGE_BYTES = 65536 + 16;     // staged input capacity (U16 blocks are < 65547 bytes)
+
+template <int HASH_LOG, bool U16, bool STAGE>
+__global__ void __launch_bounds__(32)
+lz4_compress_fast_kernel(const uint8_t* __restrict__ src_base, const uint64_t* __restrict__ src_off,
+                         const int32_t* __restrict__ src_len,
+                         uint8_t* __restrict__ dst_base, const uint64_t* __restrict__ dst_off,
+                         const int32_t* __restrict__ dst_cap, int32_t* __restrict__ result, uint32_t nblocks)
+{
+    using Entry = typename std::conditional<U16, uint16_t, uint32_t>::type;
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    Entry* table = reinterpret_cast<Entry*>(smem_raw);
+    constexpr int TABLE_BYTES = int(sizeof(Entry) << HASH_LOG);
+
+    const uint32_t b = blockIdx.x;
+    if (b >= nblocks) return;
+    const int lane = lane_id();
+    const uint8_t* __restrict__ src = src_base + src_off[b];
+    uint8_t* __restrict__ dst = dst_base + dst_off[b];
+    const int n = src_len[b];
+    const int cap = dst_cap[b];
+    int ret = 0;
+
+    if (n < 0 || n > 0x7E000000) goto done;                       // lz4.c:1324
+    if (U16 && n >= 65536 + 11) goto done;                         // lz4.c:973 (caller broke the max_src_len promise)
+    if (n == 0) {                                                  // lz4.c:1325-1336
+        if (cap >= 1) { if (lane == 0) dst[0] = 0; ret = 1; }
+        goto done;
+    }
+    for (int i = lane; i < TABLE_BYTES / 16; i += 32) reinterpret_cast<uint4*>(table)[i] = make_uint4(0, 0, 0, 0);
+    if (STAGE) {
+        // whole block -> shared memory: one TMA bulk copy (16-byte aligned part) + a lane-copied tail
+        uint8_t* stage = smem_raw + TABLE_BYTES + 16;
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(smem_raw + TABLE_BYTES);
+        const bool aligned = (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+        const int bulk = aligned ? (n & ~15) : 0;
+        if (lane == 0 && bulk) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar) : "memory");
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bulk) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         :: "r"((uint32_t)__cvta_generic_to_shared(stage)), "l"(src), "r"(bulk), "r"(bar) : "memory");
+        }
+        for (int i = bulk + lane; i < n; i += 32) stage[i] = src[i];
+        __syncwarp();
+        if (bulk) {
+            uint32_t ok;
+            do {
+                asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                             : "=r"(ok) : "r"(bar) : "memory");
+            } while (!ok);
+        }
+        __syncwarp();
+        ret = compress_block<HASH_LOG, U16>(InShared{stage}, src, n, dst, cap, table, lane);
+    } else {
+        __syncwarp();
+        ret = compress_block<HASH_LOG, U16>(InGlobal{src}, src, n, dst, cap, table, lane);
+    }
+done:
+    if (lane == 0) result[b] = ret;
+}
+
+template <int HASH_LOG, bool U16, bool STAGE>
+static cudaError_t launch_variant(const BatchArgs& a, cudaStream_t st)
+{
+    const size_t smem = ((U16 ? 2u : 4u) << HASH_LOG) + (STAGE ? 16 + STAGE_BYTES : 0);
+    auto k = lz4_compress_fast_kernel<HASH_LOG, U16, STAGE>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    // occupancy here is bounded by shared bytes per warp: take the largest carve-out
+    cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    k<<<(unsigned)a.n, 32, smem, st>>>(a.src_base, a.src_off, a.src_len, a.dst_base, a.dst_off, a.dst_cap,
+                                       a.result, (uint32_t)a.n);
+    return cudaGetLastError();
+}
+
+// tuning knobs (not part of the public header; tools/ and bench.py may set them through ctypes)
+extern "C" {
+int b200lz4_compress_hash_log = 13;   // 13 = the reference's table size for <64 KiB blocks (lz4.c:756-762)
+int b200lz4_compress_stage = 0;       // 1 = stage <=64 KiB blocks in shared memory via TMA
+}
+
+cudaError_t launch_compress_fast(const BatchArgs& a, int max_src_len, cudaStream_t st)
+{
+    if (a.n == 0) return cudaSuccess;
+    const bool u16 = max_src_len > 0 && max_src_len <= 65536;
+    if (u16) {
+        if (b200lz4_compress_stage) {
+            if (b200lz4_compress_hash_log == 12) return launch_variant<12, true, true>(a, st);
+            return launch_variant<13, true, true>(a, st);
+        }
+        if (b200lz4_compress_hash_log == 12) return launch_variant<12, true, false>(a, st);
+        if (b200lz4_compress_hash_log == 11) return launch_variant<11, true, false>(a, st);
+        return launch_variant<13, true, false>(a, st);
+    }
+    return launch_variant<12, false, false>(a, st);   // 4096 x u32 = 16 KiB, the reference's byU32 table (lz4.c:1356)
+}
+
+} // namespace b200

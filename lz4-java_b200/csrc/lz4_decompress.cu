@@ -1,0 +1,252 @@
+// lz4_decompress.cu — batch LZ4 block decompression, one independent block per warp.
+//
+// Replaces the reference's LZ4_decompress_safe (lz4.c:2345 -> 1936-2339) and
+// LZ4_decompress_fast (lz4.c:2362 -> 1794-1891) as called from the JNI shim
+// (src/jni/net_jpountz_lz4_LZ4JNI.c:216,169).  Results are bit-exact with the reference,
+// including the negative return codes of the safe decoder: the accept/reject decisions of the
+// reference's two decode loops ("fast loop" while >= 64 bytes of output room remain, then the
+// "safe loop" with its two-stage shortcut) are reproduced as decision logic; the copies are
+// warp-cooperative and never write outside [dst, dst+cap).
+//
+// Work split inside a warp: the sequence chain (token -> lengths -> offset) is inherently serial
+// and is evaluated redundantly by all 32 lanes on warp-uniform values (no divergence); the literal
+// copy and the match copy are lane-parallel.  A warp barrier orders "stores of sequence k" before
+// "match loads of sequence k+1" (matches read the block's own earlier output).
+//
+// Algorithmic HBM bytes per block: C (compressed, read once) + N (decoded, written once); match
+// sources are re-reads of freshly written output that should be served by L1/L2.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace b200 {
+
+struct VarLen { uint32_t len; int ip; bool err; };
+
+// read_variable_length (lz4.c:1903-1928): 255-chain, bounded by ilimit; ip is left where the
+// reference leaves it so that error codes agree.  Length saturates instead of overflowing.
+__device__ __forceinline__ VarLen read_varlen(const uint8_t* __restrict__ src, int ip, int ilimit, bool initial_check)
+{
+    VarLen r; r.len = 0; r.ip = ip; r.err = false;
+    if (initial_check && ip >= ilimit) { r.err = true; return r; }
+    uint32_t s;
+    do {
+        s = src[r.ip]; r.ip++;
+        r.len = min(r.len + s, 0x40000000u);
+        if (r.ip > ilimit) { r.err = true; return r; }
+    } while (s == 255);
+    return r;
+}
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+lz4_decompress_safe_kernel(const uint8_t* __restrict__ src_base, const uint64_t* __restrict__ src_off,
+                           const int32_t* __restrict__ src_len,
+                           uint8_t* dst_base, const uint64_t* __restrict__ dst_off,
+                           const int32_t* __restrict__ dst_cap, int32_t* __restrict__ result, uint32_t n)
+{
+    const uint32_t b = blockIdx.x * WARPS + (threadIdx.x >> 5);
+    if (b >= n) return;
+    const int lane = lane_id();
+    const uint8_t* __restrict__ src = src_base + src_off[b];
+    uint8_t* dst = dst_base + dst_off[b];
+    const int iend = src_len[b];
+    const int oend = dst_cap[b];
+    int ip = 0, op = 0;
+    int ret;
+
+    if (oend < 0) { ret = -1; goto done; }
+    if (oend == 0) { ret = (iend == 1 && src[0] == 0) ? 0 : -1; goto done; }          // lz4.c:1978-1982
+    if (iend <= 0) { ret = -1; goto done; }
+    {
+        bool fastloop = oend >= 64;                                                     // lz4.c:1989
+        const uint8_t* __restrict__ sl = src + lane;        // per-lane views: sl[i] == src[i + lane]
+        uint8_t* dl = dst + lane;
+        for (;;) {
+            // ---- hot loop: the reference's fast-loop common case (lz4.c:2017-2062) — short literal
+            // run, short match, far from both ends — decoded with 32-bit bookkeeping and no error
+            // exits.  Anything else (length extensions, end-of-block rules, bad offsets) drops to the
+            // general path below, which re-decodes the sequence from its token with the full rules;
+            // the literal bytes the hot loop may already have stored are simply stored again.
+            while (fastloop && ip + 18 <= iend) {                                       // token + <=14 literals + offset stay inside src
+                const uint32_t token = src[ip];
+                const uint32_t lit = token >> 4, mlc = token & 15;
+                if (lit == 15 || mlc == 15) break;
+                if (lane < lit) dl[op] = sl[ip + 1];
+                const int ipo = ip + 1 + (int)lit;
+                const uint32_t off = (uint32_t)src[ipo] | ((uint32_t)src[ipo + 1] << 8);
+                const int op2 = op + (int)lit, ml = (int)mlc + 4;
+                if (op2 + ml >= oend - 64 || off > (uint32_t)op2 || off == 0) break;
+                __syncwarp();
+                if (off >= (uint32_t)ml) { if (lane < ml) dl[op2] = dl[op2 - (int)off]; }
+                else warp_match_copy(dst + op2, (int)off, ml, lane);
+                ip = ipo + 2; op = op2 + ml;
+            }
+            const uint32_t token = src[ip++];
+            uint32_t len = token >> 4;
+            bool apply_end_rule, shortcut = false;
+            if (fastloop) {
+                bool leave;
+                if (len == 15) {                                                        // lz4.c:2003-2012
+                    VarLen v = read_varlen(src, ip, iend - 15, true);
+                    ip = v.ip; if (v.err) goto error;
+                    len += v.len;
+                    leave = ((long long)op + len > oend - 32) || ((long long)ip + len > iend - 32);
+                } else leave = ip > iend - 17;                                          // lz4.c:2020
+                if (leave) fastloop = false;
+                apply_end_rule = leave;
+            } else {
+                shortcut = (len != 15) && (ip < iend - 16) && (op <= oend - 32);        // lz4.c:2128-2130
+                if (!shortcut && len == 15) {                                           // lz4.c:2163-2169
+                    VarLen v = read_varlen(src, ip, iend - 15, true);
+                    ip = v.ip; if (v.err) goto error;
+                    len += v.len;
+                }
+                apply_end_rule = !shortcut;
+            }
+            const long long lcpy = (long long)op + len;
+            if (apply_end_rule && (lcpy > oend - 12 || (long long)ip + len > iend - 8)) {
+                // must be the last sequence (lz4.c:2175-2213)
+                if ((long long)ip + len != iend || lcpy > oend) goto error;
+                warp_copy(dst + op, src + ip, (int)len, lane);
+                op += (int)len;
+                break;
+            }
+            warp_copy(dst + op, src + ip, (int)len, lane);
+            ip += (int)len; op += (int)len;
+
+            const int off = src[ip] | (src[ip + 1] << 8);
+            ip += 2;
+            uint32_t ml = token & 15;
+            const bool direct = shortcut && ml != 15 && off >= 8 && off <= op;          // lz4.c:2144-2155
+            if (ml == 15) {                                                             // lz4.c:2036, 2236
+                VarLen v = read_varlen(src, ip, iend - 4, false);
+                ip = v.ip; if (v.err) goto error;
+                ml += v.len;
+            }
+            ml += 4;
+            if (!direct) {
+                if (off > op) goto error;                                               // lz4.c:2041,2066,2247
+                const long long mcpy = (long long)op + ml;
+                if (fastloop && mcpy >= oend - 64) fastloop = false;                    // lz4.c:2043,2048
+                if (mcpy > oend - 5) goto error;                                        // lz4.c:2317
+            }
+            __syncwarp();
+            if (off == 0) {
+                // not rejected by the reference; its small-offset path seeds the copy with zeros
+                // (lz4.c:479, 2301), so the whole match expands to 0x00.
+                for (int i = lane; i < (int)ml; i += 32) dst[op + i] = 0;
+            } else {
+                warp_match_copy(dst + op, off, (int)ml, lane);
+            }
+            op += (int)ml;
+        }
+        ret = op;
+        goto done;
+    }
+error:
+    ret = -ip - 1;                                                                      // lz4.c:2337
+done:
+    if (lane == 0) result[b] = ret;
+}
+
+// LZ4_decompress_fast: knows the exact decoded size, trusts the input (lz4.c:1794-1891); every
+// error is -1, success returns the number of compressed bytes consumed.  Unlike the reference this
+// kernel also knows how many source bytes are readable (`avail`) and reports -1 instead of reading
+// past them — the only deviation, and only on malformed input.
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+lz4_decompress_fast_kernel(const uint8_t* __restrict__ src_base, const uint64_t* __restrict__ src_off,
+                           const int32_t* __restrict__ src_avail,
+                           uint8_t* dst_base, const uint64_t* __restrict__ dst_off,
+                           const int32_t* __restrict__ dst_len, int32_t* __restrict__ result, uint32_t n)
+{
+    const uint32_t b = blockIdx.x * WARPS + (threadIdx.x >> 5);
+    if (b >= n) return;
+    const int lane = lane_id();
+    const uint8_t* __restrict__ src = src_base + src_off[b];
+    uint8_t* dst = dst_base + dst_off[b];
+    const int avail = src_avail[b];
+    const int oend = dst_len[b];
+    int ip = 0, op = 0, ret = -1;
+
+    if (oend < 0) goto done;
+    for (;;) {
+        {   // hot loop: short literal run + short match, away from both ends (rules below cannot fire)
+            const uint8_t* __restrict__ sl = src + lane;
+            uint8_t* dl = dst + lane;
+            while (ip + 17 <= avail) {
+                const uint32_t token = src[ip];
+                const uint32_t lit = token >> 4, mlc = token & 15;
+                if (lit == 15 || mlc == 15) break;
+                const int op2 = op + (int)lit, ml = (int)mlc + 4;
+                if (op2 + 23 > oend) break;                                             // keeps :1823,:1827,:1846,:1882 silent
+                if (lane < lit) dl[op] = sl[ip + 1];
+                const int ipo = ip + 1 + (int)lit;
+                const uint32_t off = (uint32_t)src[ipo] | ((uint32_t)src[ipo + 1] << 8);
+                if (off > (uint32_t)op2 || off == 0) break;
+                __syncwarp();
+                if (off >= (uint32_t)ml) { if (lane < ml) dl[op2] = dl[op2 - (int)off]; }
+                else warp_match_copy(dst + op2, (int)off, ml, lane);
+                ip = ipo + 2; op = op2 + ml;
+            }
+        }
+        if (ip >= avail) goto done;
+        const uint32_t token = src[ip++];
+        uint32_t ll = token >> 4;
+        if (ll == 15) {
+            uint32_t s;
+            do { if (ip >= avail) goto done; s = src[ip++]; ll = min(ll + s, 0x40000000u); } while (s == 255);
+        }
+        if ((uint32_t)(oend - op) < ll) goto done;                                      // lz4.c:1823
+        if ((long long)ip + ll > avail) goto done;
+        warp_copy(dst + op, src + ip, (int)ll, lane);
+        op += (int)ll; ip += (int)ll;
+        if (oend - op < 12) {                                                           // lz4.c:1827-1833
+            if (op == oend) { ret = ip; }
+            goto done;
+        }
+        if (ip + 2 > avail) goto done;
+        const int off = src[ip] | (src[ip + 1] << 8);
+        ip += 2;
+        uint32_t ml = token & 15;
+        if (ml == 15) {
+            uint32_t s;
+            do { if (ip >= avail) goto done; s = src[ip++]; ml = min(ml + s, 0x40000000u); } while (s == 255);
+        }
+        ml += 4;
+        if ((uint32_t)(oend - op) < ml) goto done;                                      // lz4.c:1846
+        if (off > op) goto done;                                                        // lz4.c:1851
+        __syncwarp();
+        if (off != 0) warp_match_copy(dst + op, off, (int)ml, lane);
+        else for (int i = lane; i < (int)ml; i += 32) dst[op + i] = 0;                  // off==0: the reference's op[u]=op[u] keeps whatever
+                                                                                        // the caller's buffer held (undefined content); the
+                                                                                        // device has no copy of that buffer, so emit zeros
+                                                                                        // like the safe decoder does
+        op += (int)ml;
+        if (oend - op < 5) goto done;                                                   // lz4.c:1882
+    }
+done:
+    if (lane == 0) result[b] = ret;
+}
+
+static constexpr int DEC_WARPS = 4;
+
+cudaError_t launch_decompress_safe(const BatchArgs& a, cudaStream_t st)
+{
+    if (a.n == 0) return cudaSuccess;
+    const unsigned grid = (unsigned)((a.n + DEC_WARPS - 1) / DEC_WARPS);
+    lz4_decompress_safe_kernel<DEC_WARPS><<<grid, DEC_WARPS * 32, 0, st>>>(
+        a.src_base, a.src_off, a.src_len, a.dst_base, a.dst_off, a.dst_cap, a.result, (uint32_t)a.n);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_decompress_fast(const BatchArgs& a, cudaStream_t st)
+{
+    if (a.n == 0) return cudaSuccess;
+    const unsigned grid = (unsigned)((a.n + DEC_WARPS - 1) / DEC_WARPS);
+    lz4_decompress_fast_kernel<DEC_WARPS><<<grid, DEC_WARPS * 32, 0, st>>>(
+        a.src_base, a.src_off, a.src_len, a.dst_base, a.dst_off, a.dst_cap, a.result, (uint32_t)a.n);
+    return cudaGetLastError();
+}
+
+} // namespace b200

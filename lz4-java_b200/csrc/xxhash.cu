@@ -1,0 +1,293 @@
+// xxhash.cu — batch XXH32 / XXH64 (xxHash 0.6.5 semantics), one buffer per lane.
+//
+// Replaces the reference's XXH32 / XXH64 one-shots (xxhash.c:392-416 -> 351-389, 855-879 ->
+// 810-852; JNI call sites src/jni/net_jpountz_xxhash_XXHashJNI.c:54,78,164,188) and the streaming
+// state machine (xxhash.c:437-563, 898-1016; JNI :89-145, :199-255).  Bit-exact.
+//
+// The stripe loop of one buffer is a serial chain per accumulator (acc = rotl(acc + w*P2, r) * P1),
+// so the parallelism is across buffers: every lane owns one buffer and keeps the four accumulators
+// in registers (4-way ILP).  The loads are the problem: lane-per-buffer reads are strided by the
+// buffer size, so instead each warp streams its 32 buffers through shared memory with TMA bulk
+// copies (cp.async.bulk.shared.global, one per lane and chunk, completion on a per-warp mbarrier,
+// two stages): HBM sees full-line sequential reads, lanes read their own slot with conflict-free
+// 16-byte LDS (slot stride CHUNK+16).  Buffers that are not 16-byte aligned take a direct-load path.
+//
+// Algorithmic HBM bytes per buffer: len + 4 (XXH32) / len + 8 (XXH64).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace b200 {
+
+static constexpr uint32_t P32_1 = 2654435761u, P32_2 = 2246822519u, P32_3 = 3266489917u,
+                          P32_4 = 668265263u, P32_5 = 374761393u;
+static constexpr uint64_t P64_1 = 11400714785074694791ull, P64_2 = 14029467366897019727ull,
+                          P64_3 = 1609587929392839161ull, P64_4 = 9650029242287828579ull,
+                          P64_5 = 2870177450012600261ull;
+
+__device__ __forceinline__ uint32_t rotl32(uint32_t x, int r) { return __funnelshift_l(x, x, r); }
+__device__ __forceinline__ uint64_t rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
+__device__ __forceinline__ uint32_t round32(uint32_t acc, uint32_t w) { return rotl32(acc + w * P32_2, 13) * P32_1; }  // xxhash.c:269-275
+__device__ __forceinline__ uint64_t round64(uint64_t acc, uint64_t w) { return rotl64(acc + w * P64_2, 31) * P64_1; }  // xxhash.c:672-678
+__device__ __forceinline__ uint64_t merge64(uint64_t h, uint64_t v) { return (h ^ round64(0, v)) * P64_1 + P64_4; }    // xxhash.c:680-686
+
+__device__ __forceinline__ uint64_t load_u64_unaligned(const uint8_t* p)
+{
+    return uint64_t(load_u32_unaligned(p)) | (uint64_t(load_u32_unaligned(p + 4)) << 32);
+}
+
+// xxhash.c:290-348 (tail of < 16 bytes, then avalanche :278-286)
+__device__ __forceinline__ uint32_t finish32(uint32_t h, const uint8_t* p, uint32_t rem)
+{
+    while (rem >= 4) { h = rotl32(h + load_u32_unaligned(p) * P32_3, 17) * P32_4; p += 4; rem -= 4; }
+    while (rem)      { h = rotl32(h + uint32_t(*p++) * P32_5, 11) * P32_1; rem--; }
+    h ^= h >> 15; h *= P32_2; h ^= h >> 13; h *= P32_3; h ^= h >> 16;
+    return h;
+}
+// xxhash.c:701-808 (tail of < 32 bytes, then avalanche :688-696)
+__device__ __forceinline__ uint64_t finish64(uint64_t h, const uint8_t* p, uint32_t rem)
+{
+    while (rem >= 8) { h = rotl64(h ^ round64(0, load_u64_unaligned(p)), 27) * P64_1 + P64_4; p += 8; rem -= 8; }
+    if (rem >= 4)    { h = rotl64(h ^ (uint64_t(load_u32_unaligned(p)) * P64_1), 23) * P64_2 + P64_3; p += 4; rem -= 4; }
+    while (rem)      { h = rotl64(h ^ (uint64_t(*p++) * P64_5), 11) * P64_1; rem--; }
+    h ^= h >> 33; h *= P64_2; h ^= h >> 29; h *= P64_3; h ^= h >> 32;
+    return h;
+}
+
+// ---- mbarrier / TMA bulk-copy primitives (PTX; SASS: SYNCS.*, UBLKCP)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{ asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
+{ asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst_smem, const void* src_gmem, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst_smem), "l"(src_gmem), "r"(bytes), "r"(bar) : "memory");
+}
+
+template <int BITS> struct XxhTraits;
+template <> struct XxhTraits<32> { using word = uint32_t; static constexpr int STRIPE = 16; };
+template <> struct XxhTraits<64> { using word = uint64_t; static constexpr int STRIPE = 32; };
+
+template <int BITS> struct Acc;
+template <> struct Acc<32> {
+    uint32_t v1, v2, v3, v4;
+    __device__ __forceinline__ void init(uint32_t seed) { v1 = seed + P32_1 + P32_2; v2 = seed + P32_2; v3 = seed; v4 = seed - P32_1; }
+    __device__ __forceinline__ void stripe(uint4 q) { v1 = round32(v1, q.x); v2 = round32(v2, q.y); v3 = round32(v3, q.z); v4 = round32(v4, q.w); }
+    __device__ __forceinline__ void stripe_g(const uint8_t* p) {
+        stripe(make_uint4(load_u32_unaligned(p), load_u32_unaligned(p + 4), load_u32_unaligned(p + 8), load_u32_unaligned(p + 12)));
+    }
+    __device__ __forceinline__ uint32_t merge() const { return rotl32(v1, 1) + rotl32(v2, 7) + rotl32(v3, 12) + rotl32(v4, 18); }
+};
+template <> struct Acc<64> {
+    uint64_t v1, v2, v3, v4;
+    __device__ __forceinline__ void init(uint64_t seed) { v1 = seed + P64_1 + P64_2; v2 = seed + P64_2; v3 = seed; v4 = seed - P64_1; }
+    __device__ __forceinline__ void stripe(uint4 a, uint4 b) {
+        v1 = round64(v1, uint64_t(a.x) | (uint64_t(a.y) << 32)); v2 = round64(v2, uint64_t(a.z) | (uint64_t(a.w) << 32));
+        v3 = round64(v3, uint64_t(b.x) | (uint64_t(b.y) << 32)); v4 = round64(v4, uint64_t(b.z) | (uint64_t(b.w) << 32));
+    }
+    __device__ __forceinline__ void stripe_g(const uint8_t* p) {
+        v1 = round64(v1, load_u64_unaligned(p)); v2 = round64(v2, load_u64_unaligned(p + 8));
+        v3 = round64(v3, load_u64_unaligned(p + 16)); v4 = round64(v4, load_u64_unaligned(p + 24));
+    }
+    __device__ __forceinline__ uint64_t merge() const {
+        uint64_t h = rotl64(v1, 1) + rotl64(v2, 7) + rotl64(v3, 12) + rotl64(v4, 18);
+        h = merge64(h, v1); h = merge64(h, v2); h = merge64(h, v3); h = merge64(h, v4);
+        return h;
+    }
+};
+
+static constexpr int XXH_WARPS = 4;
+static constexpr int XXH_CHUNK = 256;                    // bytes per lane per stage
+static constexpr int XXH_SLOT  = XXH_CHUNK + 16;         // slot stride: 16-byte LDS conflict-free
+static constexpr int XXH_STAGES = 2;
+static constexpr size_t XXH_SMEM = size_t(XXH_WARPS) * XXH_STAGES * 32 * XXH_SLOT + 64;
+
+template <int BITS>
+__global__ void __launch_bounds__(XXH_WARPS * 32)
+xxh_batch_kernel(const uint8_t* __restrict__ base, const uint64_t* __restrict__ off, const int32_t* __restrict__ len,
+                 typename XxhTraits<BITS>::word seed, typename XxhTraits<BITS>::word* __restrict__ out, uint32_t n)
+{
+    using word = typename XxhTraits<BITS>::word;
+    constexpr int STRIPE = XxhTraits<BITS>::STRIPE;
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int warp = threadIdx.x >> 5, lane = lane_id();
+    const uint32_t first = (blockIdx.x * XXH_WARPS + warp) * 32;
+    if (first >= n) return;
+    const uint32_t i = first + lane;
+    const bool live = i < n;
+
+    const uint8_t* p = live ? base + off[i] : base;
+    const uint32_t L = live ? (uint32_t)max(len[i], 0) : 0u;
+    const uint32_t bulk = L & ~uint32_t(STRIPE - 1);                // whole stripes
+    Acc<BITS> acc; acc.init(seed);
+
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem);             // XXH_WARPS * XXH_STAGES mbarriers
+    uint8_t* slots = smem + 64 + size_t(warp) * XXH_STAGES * 32 * XXH_SLOT;
+    const bool aligned = (reinterpret_cast<uintptr_t>(p) & 15) == 0 || bulk == 0;
+
+    if (__all_sync(B200_FULL, aligned)) {
+        const uint32_t bar0 = smem_u32(&bars[warp * XXH_STAGES]);
+        if (lane == 0) {
+            for (int s = 0; s < XXH_STAGES; s++) mbar_init(bar0 + 8 * s, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        const uint32_t nchunks = (bulk + XXH_CHUNK - 1) / XXH_CHUNK;
+        const uint32_t maxchunks = __reduce_max_sync(B200_FULL, nchunks);
+
+        auto issue = [&](uint32_t k) {                              // chunk k -> stage k % STAGES
+            const uint32_t s = k % XXH_STAGES;
+            const uint32_t bytes = k < nchunks ? min(uint32_t(XXH_CHUNK), bulk - k * XXH_CHUNK) : 0u;
+            const uint32_t total = __reduce_add_sync(B200_FULL, bytes);
+            if (lane == 0) mbar_arrive_expect_tx(bar0 + 8 * s, total);
+            if (bytes) tma_bulk_g2s(smem_u32(slots + (size_t(s) * 32 + lane) * XXH_SLOT), p + size_t(k) * XXH_CHUNK, bytes, bar0 + 8 * s);
+        };
+        for (uint32_t k = 0; k < XXH_STAGES && k < maxchunks; k++) issue(k);
+        for (uint32_t k = 0; k < maxchunks; k++) {
+            const uint32_t s = k % XXH_STAGES;
+            mbar_wait(bar0 + 8 * s, (k / XXH_STAGES) & 1);
+            if (k < nchunks) {
+                const uint32_t bytes = min(uint32_t(XXH_CHUNK), bulk - k * XXH_CHUNK);
+                const uint4* q = reinterpret_cast<const uint4*>(slots + (size_t(s) * 32 + lane) * XXH_SLOT);
+                if constexpr (BITS == 32) {
+                    #pragma unroll 4
+                    for (uint32_t j = 0; j < bytes / 16; j++) acc.stripe(q[j]);
+                } else {
+                    #pragma unroll 4
+                    for (uint32_t j = 0; j < bytes / 32; j++) acc.stripe(q[2 * j], q[2 * j + 1]);
+                }
+            }
+            __syncwarp();                                           // every lane is done with stage s
+            if (k + XXH_STAGES < maxchunks) issue(k + XXH_STAGES);
+        }
+    } else {
+        for (uint32_t o = 0; o < bulk; o += STRIPE) acc.stripe_g(p + o);
+    }
+
+    if (live) {
+        if constexpr (BITS == 32) {
+            uint32_t h = (L >= 16u) ? acc.merge() : seed + P32_5;
+            out[i] = finish32(h + L, p + bulk, L - bulk);
+        } else {
+            uint64_t h = (L >= 32u) ? acc.merge() : seed + P64_5;
+            out[i] = finish64(h + uint64_t(L), p + bulk, L - bulk);
+        }
+    }
+}
+
+cudaError_t launch_xxh32(const uint8_t* base, const uint64_t* off, const int32_t* len, uint32_t seed,
+                         uint32_t* out, size_t n, cudaStream_t st)
+{
+    if (n == 0) return cudaSuccess;
+    auto k = xxh_batch_kernel<32>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XXH_SMEM);
+    if (e != cudaSuccess) return e;
+    const unsigned grid = (unsigned)((n + XXH_WARPS * 32 - 1) / (XXH_WARPS * 32));
+    k<<<grid, XXH_WARPS * 32, XXH_SMEM, st>>>(base, off, len, seed, out, (uint32_t)n);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_xxh64(const uint8_t* base, const uint64_t* off, const int32_t* len, uint64_t seed,
+                         uint64_t* out, size_t n, cudaStream_t st)
+{
+    if (n == 0) return cudaSuccess;
+    auto k = xxh_batch_kernel<64>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XXH_SMEM);
+    if (e != cudaSuccess) return e;
+    const unsigned grid = (unsigned)((n + XXH_WARPS * 32 - 1) / (XXH_WARPS * 32));
+    k<<<grid, XXH_WARPS * 32, XXH_SMEM, st>>>(base, off, len, seed, out, (uint32_t)n);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ streaming state (device-resident)
+// One lane walks the XXH32_update / XXH64_update state machine (xxhash.c:515-546, 971-1002); the
+// serial dependency makes more lanes pointless.  reset / digest are the same kernel with op codes.
+__global__ void xxh32_stream_kernel(Xxh32State* s, int op, uint32_t seed, const uint8_t* __restrict__ p, size_t len)
+{
+    if (threadIdx.x != 0) return;
+    if (op == XXH_OP_RESET) {
+        s->total = 0; s->memsize = 0; s->seed = seed;
+        s->v[0] = seed + P32_1 + P32_2; s->v[1] = seed + P32_2; s->v[2] = seed; s->v[3] = seed - P32_1;
+        return;
+    }
+    if (op == XXH_OP_UPDATE) {
+        const uint8_t* end = p + len;
+        s->total += len;
+        if (s->memsize + len < 16) { for (size_t i = 0; i < len; i++) s->mem[s->memsize + i] = p[i]; s->memsize += (uint32_t)len; return; }
+        Acc<32> a; a.v1 = s->v[0]; a.v2 = s->v[1]; a.v3 = s->v[2]; a.v4 = s->v[3];
+        if (s->memsize) {
+            const uint32_t fill = 16 - s->memsize;
+            for (uint32_t i = 0; i < fill; i++) s->mem[s->memsize + i] = p[i];
+            a.stripe_g(s->mem); p += fill; s->memsize = 0;
+        }
+        while (p + 16 <= end) { a.stripe_g(p); p += 16; }
+        s->v[0] = a.v1; s->v[1] = a.v2; s->v[2] = a.v3; s->v[3] = a.v4;
+        uint32_t r = 0; while (p < end) s->mem[r++] = *p++;
+        s->memsize = r;
+        return;
+    }
+    {   // digest (xxhash.c:548-563): non-destructive
+        uint32_t h;
+        if (s->total >= 16) h = rotl32(s->v[0], 1) + rotl32(s->v[1], 7) + rotl32(s->v[2], 12) + rotl32(s->v[3], 18);
+        else h = s->seed + P32_5;
+        h += (uint32_t)s->total;
+        s->digest = finish32(h, s->mem, s->memsize);
+    }
+}
+
+__global__ void xxh64_stream_kernel(Xxh64State* s, int op, uint64_t seed, const uint8_t* __restrict__ p, size_t len)
+{
+    if (threadIdx.x != 0) return;
+    if (op == XXH_OP_RESET) {
+        s->total = 0; s->memsize = 0; s->seed = seed;
+        s->v[0] = seed + P64_1 + P64_2; s->v[1] = seed + P64_2; s->v[2] = seed; s->v[3] = seed - P64_1;
+        return;
+    }
+    if (op == XXH_OP_UPDATE) {
+        const uint8_t* end = p + len;
+        s->total += len;
+        if (s->memsize + len < 32) { for (size_t i = 0; i < len; i++) s->mem[s->memsize + i] = p[i]; s->memsize += (uint32_t)len; return; }
+        Acc<64> a; a.v1 = s->v[0]; a.v2 = s->v[1]; a.v3 = s->v[2]; a.v4 = s->v[3];
+        if (s->memsize) {
+            const uint32_t fill = 32 - s->memsize;
+            for (uint32_t i = 0; i < fill; i++) s->mem[s->memsize + i] = p[i];
+            a.stripe_g(s->mem); p += fill; s->memsize = 0;
+        }
+        while (p + 32 <= end) { a.stripe_g(p); p += 32; }
+        s->v[0] = a.v1; s->v[1] = a.v2; s->v[2] = a.v3; s->v[3] = a.v4;
+        uint32_t r = 0; while (p < end) s->mem[r++] = *p++;
+        s->memsize = r;
+        return;
+    }
+    {
+        uint64_t h;
+        if (s->total >= 32) {
+            h = rotl64(s->v[0], 1) + rotl64(s->v[1], 7) + rotl64(s->v[2], 12) + rotl64(s->v[3], 18);
+            for (int k = 0; k < 4; k++) h = merge64(h, s->v[k]);
+        } else h = s->seed + P64_5;
+        h += s->total;
+        s->digest = finish64(h, s->mem, s->memsize);
+    }
+}
+
+cudaError_t launch_xxh32_stream(Xxh32State* st, int op, uint32_t seed, const uint8_t* data, size_t len, cudaStream_t s)
+{
+    xxh32_stream_kernel<<<1, 32, 0, s>>>(st, op, seed, data, len);
+    return cudaGetLastError();
+}
+cudaError_t launch_xxh64_stream(Xxh64State* st, int op, uint64_t seed, const uint8_t* data, size_t len, cudaStream_t s)
+{
+    xxh64_stream_kernel<<<1, 32, 0, s>>>(st, op, seed, data, len);
+    return cudaGetLastError();
+}
+
+} // namespace b200

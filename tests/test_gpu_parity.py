@@ -1,0 +1,291 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded
+inputs.  Decompression and hashes must be bit-exact (including negative return codes of the safe
+decoder); compression must emit a valid LZ4 block that the oracle decodes back to the input."""
+import random
+
+import numpy as np
+import pytest
+
+import corpus
+
+pytestmark = pytest.mark.gpu
+
+
+def _slots(lens, extra=0, align=16):
+    caps = [int(x) + extra for x in lens]
+    offs, pos = [], 0
+    for c in caps:
+        offs.append(pos)
+        pos += (c + align - 1) // align * align + align
+    return np.array(offs, dtype=np.uint64), np.array(caps, dtype=np.int32), pos + 64
+
+
+def test_decompress_safe_exact(b200, checker):
+    items = corpus.blocks(checker) + corpus.calgary_blocks()
+    comp = [checker.compress(d) for _, d in items]
+    src, soff, slen = corpus.pack(comp)
+    doff, dcap, total = _slots([len(d) for _, d in items])
+    dst = np.full(total, 0xAA, dtype=np.uint8)
+    res = b200.batch.decompress_safe_batch_host(src, soff, slen, dst, doff, dcap)
+    for k, (name, d) in enumerate(items):
+        assert res[k] == len(d), (name, res[k], len(d))
+        assert dst[int(doff[k]):int(doff[k]) + len(d)].tobytes() == d, name
+        # nothing written past the slot capacity
+        assert (dst[int(doff[k]) + len(d):int(doff[k]) + len(d) + 16] == 0xAA).all(), name
+
+
+def test_decompress_fast_exact(b200, checker):
+    items = corpus.blocks(checker) + corpus.calgary_blocks()
+    comp = [checker.compress(d) for _, d in items]
+    src, soff, slen = corpus.pack(comp)
+    doff, dlen, total = _slots([len(d) for _, d in items])
+    dst = np.full(total, 0xAA, dtype=np.uint8)
+    res = b200.batch.decompress_fast_batch_host(src, soff, slen, dst, doff, dlen)
+    for k, (name, d) in enumerate(items):
+        assert res[k] == len(comp[k]), (name, res[k], len(comp[k]))       # bytes READ (LZ4Test.java:185)
+        assert dst[int(doff[k]):int(doff[k]) + len(d)].tobytes() == d, name
+        assert (dst[int(doff[k]) + len(d):int(doff[k]) + len(d) + 16] == 0xAA).all(), name
+
+
+def test_decompress_safe_malformed_codes(b200, checker):
+    """Same accept/reject set AND same negative codes as the reference (lz4.c:2337)."""
+    rng = random.Random(99)
+    cases = []                                           # (compressed bytes, capacity)
+    for name, d in corpus.blocks(checker, big=False):
+        c = checker.compress(d)
+        n = len(d)
+        for cap in (n, n - 1, n + 1, n + 7, n + 64, n + 100, max(0, n - 13), 0, n // 2):
+            cases.append((c, cap))
+        for cut in (1, 2, 3, 5, 8, 13):
+            if len(c) > cut:
+                cases.append((c[:-cut], n))
+        cases.append((c + b"\0", n))
+        cases.append((c + b"\x10\x41", n))
+        for m in corpus.mutate(c, rng, 12):
+            cases.append((m, rng.choice([n, n, n + 1, n - 1, n + 70, max(0, n - 5)])))
+    for v in corpus.MALFORMED:
+        for cap in (20, 64, 100, 200):
+            cases.append((v, cap))
+    cases = [(c, cap) for c, cap in cases if len(c) > 0]
+    src, soff, slen = corpus.pack([c for c, _ in cases], pad=8)
+    doff, dcap, total = _slots([cap for _, cap in cases])
+    dst = np.zeros(total, dtype=np.uint8)
+    res = b200.batch.decompress_safe_batch_host(src, soff, slen, dst, doff, dcap)
+    negatives = 0
+    for k, (c, cap) in enumerate(cases):
+        want, out = checker.decompress_safe(c, cap)
+        assert res[k] == want, (k, len(c), cap, int(res[k]), want, c[:24].hex())
+        if want >= 0:
+            assert dst[int(doff[k]):int(doff[k]) + want].tobytes() == out, k
+        else:
+            negatives += 1
+    assert negatives > 100
+
+
+def test_decompress_fast_malformed(b200, checker):
+    rng = random.Random(7)
+    cases = []
+    for name, d in corpus.blocks(checker, big=False):
+        c = checker.compress(d)
+        n = len(d)
+        for dl in (n, n - 1, n + 1, n + 5, max(0, n - 12)):          # LZ4Test.java:209-226
+            cases.append((c, dl))
+        for m in corpus.mutate(c, rng, 6):
+            cases.append((m, n))
+    for v in corpus.MALFORMED:
+        cases.append((v, 20))
+    cases = [(c, dl) for c, dl in cases if len(c) > 0]
+    # give every stream generous zero padding so the reference's unbounded reads stay defined
+    padded = [c + bytes(dl + dl // 255 + 64) for c, dl in cases]
+    src, soff, slen = corpus.pack(padded)
+    doff, dlen, total = _slots([dl for _, dl in cases])
+    dst = np.zeros(total, dtype=np.uint8)
+    res = b200.batch.decompress_fast_batch_host(src, soff, slen, dst, doff, dlen)
+    for k, (c, dl) in enumerate(cases):
+        want, out = checker.decompress_fast(c, dl)
+        assert res[k] == want, (k, len(c), dl, int(res[k]), want)
+        if want >= 0:
+            assert dst[int(doff[k]):int(doff[k]) + dl].tobytes() == out, k
+
+
+def _knob(b200, name, value):
+    import ctypes
+    ctypes.c_int.in_dll(b200._native.lib(), name).value = value
+
+
+@pytest.mark.parametrize("table", ["u16", "u16_hl12", "u16_tma_staged", "u32"])
+def test_compress_roundtrip_through_oracle(b200, checker, table):
+    items = corpus.blocks(checker) + corpus.calgary_blocks()
+    if table != "u32":                      # 16-bit position table: caller promises blocks <= 64 KiB
+        items = [(nm, d) for nm, d in items if len(d) <= 65536]
+    max_src_len = 0 if table == "u32" else 65536
+    _knob(b200, "b200lz4_compress_hash_log", 12 if table == "u16_hl12" else 13)
+    _knob(b200, "b200lz4_compress_stage", 1 if table == "u16_tma_staged" else 0)
+    try:
+        _compress_roundtrip(b200, checker, items, max_src_len, slack=1.25 if table == "u16_hl12" else 1.10)
+    finally:
+        _knob(b200, "b200lz4_compress_hash_log", 13)
+        _knob(b200, "b200lz4_compress_stage", 0)
+
+
+def _compress_roundtrip(b200, checker, items, max_src_len, slack):
+    src, soff, slen = corpus.pack([d for _, d in items])
+    bounds = [b200.max_compressed_length(len(d)) for _, d in items]
+    doff, dcap, total = _slots(bounds)
+    dst = np.full(total, 0x55, dtype=np.uint8)
+    res = b200.batch.compress_fast_batch_host(src, soff, slen, dst, doff, dcap, max_src_len=max_src_len)
+    tot_c = tot_ref = 0
+    for k, (name, d) in enumerate(items):
+        assert 0 < res[k] <= bounds[k], (name, res[k])
+        c = dst[int(doff[k]):int(doff[k]) + int(res[k])].tobytes()
+        r, out = checker.decompress_safe(c, len(d))
+        assert r == len(d) and out == d, (name, r, len(d))
+        r2, out2 = checker.decompress_fast(c, len(d))
+        assert r2 == len(c) and out2 == d, name
+        assert dst[int(doff[k]) + bounds[k]] == 0x55, name           # nothing written past the slot
+        tot_c += len(c)
+        tot_ref += len(checker.compress(d))
+    # same ballpark as the reference's ratio on this mixed corpus
+    assert tot_c < slack * tot_ref, (tot_c, tot_ref)
+
+
+def test_compress_large_blocks_u32_table(b200, checker):
+    """blocks > 64 KiB use the 32-bit position table (lz4.c:1356 analogue)"""
+    datas = [checker.datagen(n, 0.5, 0.0, 11).tobytes() for n in (65547, 100000, 262144, 1 << 20)]
+    datas.append(b"\0" * 300000)
+    src, soff, slen = corpus.pack(datas)
+    bounds = [b200.max_compressed_length(len(d)) for d in datas]
+    doff, dcap, total = _slots(bounds)
+    dst = np.zeros(total, dtype=np.uint8)
+    res = b200.batch.compress_fast_batch_host(src, soff, slen, dst, doff, dcap, max_src_len=0)
+    for k, d in enumerate(datas):
+        c = dst[int(doff[k]):int(doff[k]) + int(res[k])].tobytes()
+        r, out = checker.decompress_safe(c, len(d))
+        assert r == len(d) and out == d, k
+        assert len(c) < 1.1 * len(checker.compress(d)) + 64
+
+
+def test_compress_limited_output(b200, checker):
+    """dst too small: 0 (-> LZ4Exception) or a valid smaller stream (LZ4Test.java:188-203)"""
+    d = checker.datagen(20000, 0.5, 0.0, 5).tobytes()
+    full = b200.LZ4Factory.b200Instance().fastCompressor().compress(d)
+    for cap in (len(full) - 1, len(full) // 2, 10, 1, 0):
+        out = bytearray(max(cap, 1))
+        try:
+            n = b200.LZ4Factory.b200Instance().fastCompressor().compress(d, 0, len(d), out, 0, cap)
+        except b200.LZ4Exception:
+            continue
+        assert n <= cap
+        r, o = checker.decompress_safe(bytes(out[:n]), len(d))
+        assert o == d
+
+
+def test_self_roundtrip_gpu_only(b200, checker):
+    """compress on GPU -> decompress on GPU (both decoders), no CPU in the loop except the compare"""
+    items = [(nm, d) for nm, d in corpus.blocks(checker) if len(d) <= 65536]
+    src, soff, slen = corpus.pack([d for _, d in items])
+    bounds = [b200.max_compressed_length(len(d)) for _, d in items]
+    coff, ccap, ctotal = _slots(bounds)
+    comp = np.zeros(ctotal, dtype=np.uint8)
+    clen = b200.batch.compress_fast_batch_host(src, soff, slen, comp, coff, ccap, max_src_len=65536)
+    doff, dcap, total = _slots(slen)
+    out = np.zeros(total, dtype=np.uint8)
+    r = b200.batch.decompress_safe_batch_host(comp, coff, clen, out, doff, dcap)
+    assert (r == slen).all()
+    out2 = np.zeros(total, dtype=np.uint8)
+    r2 = b200.batch.decompress_fast_batch_host(comp, coff, ccap, out2, doff, slen)
+    assert (r2 == clen).all()
+    for k, (name, d) in enumerate(items):
+        assert out[int(doff[k]):int(doff[k]) + len(d)].tobytes() == d, name
+        assert out2[int(doff[k]):int(doff[k]) + len(d)].tobytes() == d, name
+
+
+def test_compact_host(b200, checker):
+    datas = [checker.datagen(65536, 0.5, 0.0, s).tobytes() for s in range(40)] + [b"", b"x", b"\0" * 5000]
+    src, soff, slen = corpus.pack(datas)
+    dst = np.zeros(sum(b200.max_compressed_length(len(d)) for d in datas) + 64, dtype=np.uint8)
+    ooff, olen, total = b200.batch.compress_fast_compact_host(src, soff, slen, dst, max_src_len=65536)
+    assert total == int(olen.sum())
+    pos = 0
+    for k, d in enumerate(datas):
+        assert int(ooff[k]) == pos
+        c = dst[pos:pos + int(olen[k])].tobytes()
+        r, out = checker.decompress_safe(c, len(d))
+        assert r == len(d) and out == d
+        pos += int(olen[k])
+
+
+def test_xxhash_batches(b200, checker):
+    rng = random.Random(5)
+    bufs = [rng.randbytes(n) for n in list(range(0, 70)) + [255, 256, 257, 1000, 4096, 4097, 65536, 100001]]
+    for align, pad in ((16, 0), (1, 3)):                 # TMA path (16-byte aligned) and direct path
+        buf, off, ln = corpus.pack(bufs, align=align, pad=pad)
+        for seed in (0, 0x9747B28C, 0xFFFFFFFF):
+            h32 = b200.batch.xxh32_batch_host(buf, off, ln, seed)
+            h64 = b200.batch.xxh64_batch_host(buf, off, ln, seed * 0x100000001)
+            for k, bts in enumerate(bufs):
+                assert int(h32[k]) == checker.xxh32(bts, seed), (align, len(bts), seed)
+                assert int(h64[k]) == checker.xxh64(bts, seed * 0x100000001), (align, len(bts), seed)
+
+
+def test_xxhash_uniform_4k(b200, checker):
+    n = 3000
+    data = np.frombuffer(random.Random(3).randbytes(n * 4096), dtype=np.uint8).copy()
+    off, ln = b200.batch.uniform_layout(n, 4096)
+    h64 = b200.batch.xxh64_batch_host(data, off, ln, 0)
+    h32 = b200.batch.xxh32_batch_host(data, off, ln, 0x9747B28C)
+    for k in range(0, n, 37):
+        blk = data[k * 4096:(k + 1) * 4096]
+        assert int(h64[k]) == checker.xxh64(blk, 0)
+        assert int(h32[k]) == checker.xxh32(blk, 0x9747B28C)
+
+
+def test_xxhash_streaming(b200, checker):
+    """random chunking + resets, like XXHash32Test.java:31-75"""
+    rng = random.Random(11)
+    f = b200.XXHashFactory.b200Instance()
+    for bits, mk in ((32, f.newStreamingHash32), (64, f.newStreamingHash64)):
+        for _ in range(6):
+            data = rng.randbytes(rng.randrange(0, 5000))
+            seed = rng.randrange(1 << 31)
+            h = mk(seed)
+            h.update(rng.randbytes(50))
+            h.reset()
+            pos = 0
+            while pos < len(data):
+                step = rng.randrange(1, 600)
+                h.update(data, pos, min(step, len(data) - pos))
+                pos += step
+                if rng.random() < 0.3:
+                    h.getValue()                       # digest must be callable mid-stream
+            want = checker.xxh32(data, seed) if bits == 32 else checker.xxh64(data, seed)
+            assert h.getValue() == want
+            h.close()
+
+
+def test_factory_api_contract(b200, checker):
+    """per-call contract of LZ4Test.java:170-256 through the mirrored API"""
+    F = b200.LZ4Factory.b200Instance()
+    comp, fast, safe = F.fastCompressor(), F.fastDecompressor(), F.safeDecompressor()
+    for name, d in corpus.blocks(checker, big=False)[:40]:
+        n = len(d)
+        buf = bytearray(comp.maxCompressedLength(n))
+        clen = comp.compress(d, 0, n, buf, 0, len(buf)) if n else comp.compress(b"", 0, 0, buf, 0, len(buf))
+        c = bytes(buf[:clen])
+        if n == 0:
+            assert c == b"\x00"                                     # LZ4Test.java:111-114
+        out = bytearray(n + 1)
+        assert fast.decompress(c, 0, out, 0, n) == clen            # bytes read (:185)
+        assert bytes(out[:n]) == d
+        out = bytearray(n)
+        assert safe.decompress(c, 0, clen, out, 0, n) == n         # bytes written (:232)
+        assert bytes(out) == d
+        if n > 0:
+            with pytest.raises(b200.LZ4Exception):                  # destLen-1 must throw (:209-217)
+                fast.decompress(c, 0, bytearray(n), 0, n - 1)
+        with pytest.raises(b200.LZ4Exception):                      # srcLen+1 must throw (:240-245)
+            safe.decompress(c + b"\x00", 0, clen + 1, bytearray(n + 8), 0, n)
+    for v in corpus.MALFORMED[1:]:
+        with pytest.raises(b200.LZ4Exception):
+            safe.decompress(v, 0, len(v), bytearray(64), 0, 64)
+    safe.decompress(corpus.MALFORMED[0], 0, len(corpus.MALFORMED[0]), bytearray(64), 0, 64)   # must not throw or hang
