@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libb200lz4.so")
+SO_PATH = os.environ.get("B200LZ4_SO") or os.path.join(_HERE, "libb200lz4.so")   # env override: sanitizer builds
 
 E_NODEVICE, E_CUDA, E_ARG = -1000001, -1000002, -1000003
 

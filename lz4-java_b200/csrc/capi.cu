@@ -47,6 +47,8 @@ struct Slot {
     cudaEvent_t done = nullptr;
     uint8_t *d_src = nullptr, *d_dst = nullptr; size_t src_cap = 0, dst_cap = 0;
     uint8_t* d_aux = nullptr; size_t aux_cap = 0;      // compacted output (compact_host only)
+    uint8_t* h_out = nullptr; size_t h_out_cap = 0;    // pinned bounce for scattered dst slots
+    bool scatter = false;                              // retire must copy h_out -> caller slots
     cudaEvent_t drained = nullptr; bool draining = false;
     // descriptors: [total | soff | doff | xoff] u64, [slen | dcap | res] i32 — one pinned and one device copy
     uint8_t *h_desc = nullptr, *d_desc = nullptr; size_t desc_blocks = 0;
@@ -70,7 +72,8 @@ struct Slot {
 };
 
 static constexpr int    NSLOTS = 3;
-static constexpr size_t CHUNK_SPAN = size_t(32) << 20;     // bytes of src (and of dst) per pipeline chunk
+static constexpr size_t CHUNK_SPAN = size_t(256) << 20;    // bytes of src (and of dst) per pipeline chunk: >= 4096 64-KiB blocks,
+                                                           // i.e. at least two full waves of warps on 148 SMs per launch
 static constexpr size_t CHUNK_BLOCKS = 1 << 16;
 
 struct Ctx {
@@ -149,12 +152,20 @@ static cudaError_t launch_op(Op op, const BatchArgs& a, int param, cudaStream_t 
     }
 }
 
-// finish the slot's in-flight chunk: wait, hand the per-block results to the caller
-static int slot_retire(Slot& s, int32_t* result)
+// finish the slot's in-flight chunk: wait, hand the per-block results (and, for scattered dst
+// layouts, the bytes staged in the pinned bounce buffer) to the caller
+static int slot_retire(Slot& s, int32_t* result, uint8_t* dst_base = nullptr, const uint64_t* dst_off = nullptr,
+                       const int32_t* dst_cap = nullptr)
 {
     if (!s.busy) return 0;
     CK(cudaEventSynchronize(s.done));
     memcpy(result + s.i0, s.h_res(), (s.i1 - s.i0) * sizeof(int32_t));
+    if (s.scatter && dst_base) {
+        const uint64_t d_lo = dst_off[s.i0];
+        for (size_t k = s.i0; k < s.i1; k++)
+            if (dst_cap[k] > 0) memcpy(dst_base + dst_off[k], s.h_out + (dst_off[k] - d_lo), (size_t)dst_cap[k]);
+    }
+    s.scatter = false;
     s.busy = false;
     return 0;
 }
@@ -189,7 +200,7 @@ static int host_batch(Op op, const uint8_t* src_base, const uint64_t* src_off, c
         const size_t nb = i1 - i0, s_span = (size_t)(s_hi - s_lo), d_span = (size_t)(d_hi - d_lo);
 
         Slot& s = c->slot[cur];
-        rc = slot_retire(s, result); if (rc) return rc;
+        rc = slot_retire(s, result, dst_base, dst_off, dst_cap); if (rc) return rc;
         rc = slot_reserve(s, s_span + 16, d_span + 16, nb); if (rc) return rc;
 
         // keep the source's 16-byte phase so aligned inputs stay aligned on the device
@@ -205,23 +216,36 @@ static int host_batch(Op op, const uint8_t* src_base, const uint64_t* src_off, c
         BatchArgs a{ s.d_src, s.d_soff(), s.d_slen(), s.d_dst, s.d_doff(), s.d_dcap(), s.d_res(), nb };
         CK(launch_op(op, a, param, s.st));
         CK(cudaMemcpyAsync(s.h_res(), s.d_res(), nb * sizeof(int32_t), cudaMemcpyDeviceToHost, s.st));
-        // copy back every maximal contiguous run of dst slots (normally the whole chunk is one run),
-        // never touching caller bytes that lie between non-adjacent slots
-        size_t r0 = 0;
-        while (r0 < nb) {
-            size_t r1 = r0 + 1;
-            uint64_t end = dst_off[i0 + r0] + (uint64_t)(dst_cap[i0 + r0] > 0 ? dst_cap[i0 + r0] : 0);
-            while (r1 < nb && dst_off[i0 + r1] == end) { end += (uint64_t)(dst_cap[i0 + r1] > 0 ? dst_cap[i0 + r1] : 0); r1++; }
-            const uint64_t beg = dst_off[i0 + r0];
-            if (end > beg)
-                CK(cudaMemcpyAsync(dst_base + beg, s.d_dst + d_phase + (beg - d_lo), (size_t)(end - beg), cudaMemcpyDeviceToHost, s.st));
-            r0 = r1;
+        // copy back: when the dst slots are back to back (the normal layout) one DMA lands straight in
+        // the caller's memory; otherwise the span goes to a pinned bounce buffer and retire() scatters
+        // the slots, so caller bytes BETWEEN non-adjacent slots are never touched
+        bool contiguous = true;
+        {
+            uint64_t end = d_lo;
+            for (size_t k = 0; k < nb && contiguous; k++) {
+                if (dst_off[i0 + k] != end) contiguous = false;
+                end = dst_off[i0 + k] + (uint64_t)(dst_cap[i0 + k] > 0 ? dst_cap[i0 + k] : 0);
+            }
+        }
+        if (d_span) {
+            if (contiguous) {
+                CK(cudaMemcpyAsync(dst_base + d_lo, s.d_dst + d_phase, d_span, cudaMemcpyDeviceToHost, s.st));
+            } else {
+                if (d_span > s.h_out_cap) {
+                    if (s.h_out) CK(cudaFreeHost(s.h_out));
+                    s.h_out = nullptr; s.h_out_cap = 0;
+                    const size_t cap = d_span + (d_span >> 2) + 4096;
+                    CK(cudaHostAlloc(&s.h_out, cap, cudaHostAllocDefault)); s.h_out_cap = cap;
+                }
+                CK(cudaMemcpyAsync(s.h_out, s.d_dst + d_phase, d_span, cudaMemcpyDeviceToHost, s.st));
+                s.scatter = true;
+            }
         }
         CK(cudaEventRecord(s.done, s.st));
         s.busy = true; s.i0 = i0; s.i1 = i1;
         i0 = i1; cur = (cur + 1) % NSLOTS;
     }
-    for (int k = 0; k < NSLOTS; k++) { rc = slot_retire(c->slot[(cur + k) % NSLOTS], result); if (rc) return rc; }
+    for (int k = 0; k < NSLOTS; k++) { rc = slot_retire(c->slot[(cur + k) % NSLOTS], result, dst_base, dst_off, dst_cap); if (rc) return rc; }
     return 0;
 }
 

@@ -27,6 +27,16 @@ __device__ __forceinline__ uint32_t load_u32_unaligned(const uint8_t* p)
     return __funnelshift_r(lo, hi, sh);
 }
 
+// Byte load that bypasses L1 (served by L2): used for LZ4 match sources, i.e. bytes this warp wrote
+// moments ago.  Stores are write-through to L2, so L2 is where the data is; skipping L1 also keeps
+// the scattered look-back lines from evicting the sequential input stream.
+__device__ __forceinline__ uint8_t load_u8_l2(const uint8_t* p)
+{
+    uint32_t v;
+    asm volatile("ld.global.cg.u8 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return uint8_t(v);
+}
+
 // Cooperative copy of n bytes between NON-overlapping ranges (or ranges whose distance is at
 // least the copy length).  32 lanes, 4 bytes per lane per iteration once dst is word-aligned.
 // `sync_each_iter` inserts a warp barrier between iterations: required when dst-src < n but

@@ -34,6 +34,19 @@ struct InGlobal {
     const uint8_t* __restrict__ p;
     __device__ __forceinline__ uint32_t ld1(int i) const { return p[i]; }
     __device__ __forceinline__ uint32_t ld4(int i) const { return load_u32_unaligned(p + i); }
+    // "far" loads: random look-backs at candidate positions.  They bypass L1 (ld.global.cg) so that
+    // 32 scattered lines per step do not evict the forward stream, which L1 is kept for.
+    __device__ __forceinline__ uint32_t ld1_far(int i) const {
+        uint32_t v; asm volatile("ld.global.cg.u8 %0, [%1];" : "=r"(v) : "l"(p + i)); return v;
+    }
+    __device__ __forceinline__ uint32_t ld4_far(int i) const {
+        const uintptr_t a = reinterpret_cast<uintptr_t>(p + i);
+        const uint32_t sh = (uint32_t(a) & 3u) * 8u;
+        uint32_t lo, hi = 0;
+        asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(lo) : "l"(a & ~uintptr_t(3)));
+        if (sh) asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(hi) : "l"((a & ~uintptr_t(3)) + 4));
+        return __funnelshift_r(lo, hi, sh);
+    }
     __device__ __forceinline__ const uint8_t* ptr(int i) const { return p + i; }
 };
 struct InShared {
@@ -46,6 +59,8 @@ struct InShared {
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(hi) : "r"((a & ~3u) + 4u));
         return __funnelshift_r(lo, hi, (a & 3u) * 8u);
     }
+    __device__ __forceinline__ uint32_t ld1_far(int i) const { return ld1(i); }
+    __device__ __forceinline__ uint32_t ld4_far(int i) const { return ld4(i); }
     __device__ __forceinline__ const uint8_t* ptr(int i) const { return p + i; }
 };
 
@@ -57,7 +72,7 @@ __device__ __forceinline__ int match_extend(const In& in, int a, int b, int maxl
     for (;;) {
         const int i = total + lane * 4;
         uint32_t x = 1;                                   // "differs at byte 0" beyond the limit
-        if (i < maxlen) x = in.ld4(a + i) ^ in.ld4(b + i);
+        if (i < maxlen) x = in.ld4(a + i) ^ in.ld4_far(b + i);
         const unsigned neq = __ballot_sync(B200_FULL, x != 0);
         if (neq) {
             const int fl = __ffs(neq) - 1;
@@ -75,7 +90,38 @@ __device__ __forceinline__ void write_len_ext(uint8_t* d, int v, int cnt, int la
     for (int i = lane; i < cnt; i += 32) d[i] = (i == cnt - 1) ? uint8_t(v - 255 * (cnt - 1)) : uint8_t(255);
 }
 
+// One LZ4 sequence waiting to be written: literals [anchor, ms) then a match of ml bytes at distance off.
+struct Seq { int anchor, ms, off, ml; };
+
+// token, [literal length], literals, offset, [match length] with lane-parallel stores.
+// Returns false if dst is too small (lz4.c:1085-1088, 1158).
+template <class In>
+__device__ __forceinline__ bool emit_sequence(const In& in, const Seq& q, uint32_t litv, uint8_t* __restrict__ dst, int& op, int cap, int lane)
+{
+    const int lit = q.ms - q.anchor;
+    const int mcode = q.ml - 4;
+    const int lhdr = lit >= 15 ? (lit - 15) / 255 + 1 : 0;
+    const int mhdr = mcode >= 15 ? (mcode - 15) / 255 + 1 : 0;
+    if ((long long)op + 1 + lhdr + lit + 2 + mhdr > cap) return false;
+    uint8_t* d = dst + op;
+    if (lane == 0) d[0] = uint8_t((min(lit, 15) << 4) | min(mcode, 15));
+    d += 1;
+    if (lhdr) { write_len_ext(d, lit - 15, lhdr, lane); d += lhdr; }
+    if (lit <= 32) { if (lane < lit) d[lane] = uint8_t(litv); }                // byte preloaded by the caller
+    else warp_copy_words<false>(d, in.ptr(q.anchor), lit, lane);
+    d += lit;
+    if (lane < 2) d[lane] = uint8_t(q.off >> (8 * lane));                       // LE16 offset (lz4.c:1133)
+    d += 2;
+    if (mhdr) { write_len_ext(d, mcode - 15, mhdr, lane); }
+    op += 1 + lhdr + lit + 2 + mhdr;
+    return true;
+}
+
 // The greedy warp parser.  Returns the compressed size, 0 if dst is too small.
+//
+// Software-pipelined by one sequence: the probe loads of step k+1 (input window, table, candidate
+// bytes) are issued BEFORE sequence k is written out, so the emission stores and literal copies fill
+// the latency of those dependent loads instead of adding to the serial chain.
 template <int HASH_LOG, bool U16, class In, class Entry>
 __device__ __forceinline__ int compress_block(const In in, const uint8_t* __restrict__ gsrc, int n,
                                               uint8_t* __restrict__ dst, int cap, Entry* table, int lane)
@@ -84,26 +130,39 @@ __device__ __forceinline__ int compress_block(const In in, const uint8_t* __rest
     const int mflimit = n - 12;        // last position a match may start at (MFLIMIT, lz4.c:243)
     const int matchlimit = n - 5;      // matches end here at the latest (LASTLITERALS, lz4.c:244)
     int pf = 0;                        // software prefetch cursor (global input only)
+    bool have = false;                 // a found-but-not-yet-written sequence
+    Seq q = {0, 0, 0, 0};
 
     while (ip <= mflimit) {            // n < 13 never finds a match: all literals (lz4.c:981)
         if (std::is_same<In, InGlobal>::value) {
             if (pf < ip + 2048) {      // keep ~4 KiB of the forward stream on its way to L2
-                const int q = pf + lane * 128;
-                if (q < n) asm volatile("prefetch.global.L2 [%0];" :: "l"(__cvta_generic_to_global(gsrc + q)));
+                const int qq = pf + lane * 128;
+                if (qq < n) asm volatile("prefetch.global.L2 [%0];" :: "l"(__cvta_generic_to_global(gsrc + qq)));
                 pf += 4096;
             }
-            if (lane < 2 && ip + 128 + lane * 128 < n)     // and the next two lines in L1
-                asm volatile("prefetch.global.L1 [%0];" :: "l"(__cvta_generic_to_global(gsrc + ip + 128 + lane * 128)));
         }
+        // ---- A: probe 32 positions; the pending sequence's literal bytes are fetched alongside
+        uint32_t litv = 0;
+        if (have && lane < q.ms - q.anchor && q.ms - q.anchor <= 32) litv = in.ld1(q.anchor + lane);
+        if (std::is_same<In, InGlobal>::value && lane == 0 && ip + 160 < n)     // next line of the forward stream -> L1
+            asm volatile("prefetch.global.L1 [%0];" :: "l"(__cvta_generic_to_global(gsrc + ip + 128)));
         const int p = ip + lane;
         const bool valid = p <= mflimit;
-        uint32_t h = 0; int cand = 0; bool hit = false;
-        if (valid) {
-            const uint32_t seq = in.ld4(p);
-            h = (seq * 2654435761u) >> (32 - HASH_LOG);
-            cand = table[h];
-            if (cand < p && (U16 || p - cand <= 65535)) hit = in.ld4(cand) == seq;
+        const int pp = min(p, mflimit);
+        const uint32_t seq = in.ld4(pp);
+        const uint32_t h = (seq * 2654435761u) >> (32 - HASH_LOG);
+        const int cand = table[h];
+        const bool plausible = valid && cand < p && (U16 || p - cand <= 65535);
+        const uint32_t cseq = in.ld4_far(plausible ? cand : pp);
+
+        // ---- B: write the previous sequence while those loads are in flight
+        if (have) {
+            if (!emit_sequence(in, q, litv, dst, op, cap, lane)) return 0;
+            have = false;
         }
+
+        // ---- C: vote, publish, extend
+        const bool hit = plausible && cseq == seq;
         const unsigned m = __ballot_sync(B200_FULL, hit);
         const int f = m ? __ffs(m) - 1 : 31;
         if (valid && lane <= f) table[h] = Entry(p);
@@ -117,7 +176,7 @@ __device__ __forceinline__ int compress_block(const In in, const uint8_t* __rest
             const int d = lane - 8;
             const int backroom = min(ms - anchor, mc);
             const bool ok = d < 0 ? (-d <= backroom) : (ms + d < matchlimit);
-            const bool eq = ok && in.ld1(ms + d) == in.ld1(mc + d);
+            const bool eq = ok && in.ld1(ms + d) == in.ld1_far(mc + d);
             const unsigned e = __ballot_sync(B200_FULL, eq);
             const int back = __clz((~e) & 0xFFu) - 24;                       // ones below bit 8, contiguous from bit 7
             const int fwd = __ffs((~(e >> 8)) | (1u << 24)) - 1;             // ones from bit 8 upwards, <= 24
@@ -125,23 +184,13 @@ __device__ __forceinline__ int compress_block(const In in, const uint8_t* __rest
             if (fwd == 24) ml += match_extend(in, ms + 24, mc + 24, matchlimit - (ms + 24), lane);
             ms -= back; mc -= back; ml += back;
         }
-
-        // ---- emit one sequence: token, [literal length], literals, offset, [match length]
-        const int lit = ms - anchor;
-        const int mcode = ml - 4;
-        const int lhdr = lit >= 15 ? (lit - 15) / 255 + 1 : 0;
-        const int mhdr = mcode >= 15 ? (mcode - 15) / 255 + 1 : 0;
-        if ((long long)op + 1 + lhdr + lit + 2 + mhdr > cap) return 0;           // lz4.c:1085-1088, 1158
-        if (lane == 0) dst[op] = uint8_t((min(lit, 15) << 4) | min(mcode, 15));
-        op += 1;
-        if (lhdr) { write_len_ext(dst + op, lit - 15, lhdr, lane); op += lhdr; }
-        warp_copy(dst + op, in.ptr(anchor), lit, lane);
-        op += lit;
-        if (lane < 2) dst[op + lane] = uint8_t((ms - mc) >> (8 * lane));          // LE16 offset (lz4.c:1133)
-        op += 2;
-        if (mhdr) { write_len_ext(dst + op, mcode - 15, mhdr, lane); op += mhdr; }
-
+        q.anchor = anchor; q.ms = ms; q.off = ms - mc; q.ml = ml; have = true;
         ip = anchor = ms + ml;
+    }
+    if (have) {
+        uint32_t litv = 0;
+        if (lane < q.ms - q.anchor && q.ms - q.anchor <= 32) litv = in.ld1(q.anchor + lane);
+        if (!emit_sequence(in, q, litv, dst, op, cap, lane)) return 0;
     }
 
     {   // last literals (lz4.c:1266-1293)

@@ -38,7 +38,7 @@ __device__ __forceinline__ VarLen read_varlen(const uint8_t* __restrict__ src, i
 }
 
 template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32)
+__global__ void __launch_bounds__(WARPS * 32, 2048 / (WARPS * 32))
 lz4_decompress_safe_kernel(const uint8_t* __restrict__ src_base, const uint64_t* __restrict__ src_off,
                            const int32_t* __restrict__ src_len,
                            uint8_t* dst_base, const uint64_t* __restrict__ dst_off,
@@ -77,7 +77,7 @@ lz4_decompress_safe_kernel(const uint8_t* __restrict__ src_base, const uint64_t*
                 const int op2 = op + (int)lit, ml = (int)mlc + 4;
                 if (op2 + ml >= oend - 64 || off > (uint32_t)op2 || off == 0) break;
                 __syncwarp();
-                if (off >= (uint32_t)ml) { if (lane < ml) dl[op2] = dl[op2 - (int)off]; }
+                if (off >= (uint32_t)ml) { if (lane < ml) dl[op2] = load_u8_l2(dl + op2 - (int)off); }
                 else warp_match_copy(dst + op2, (int)off, ml, lane);
                 ip = ipo + 2; op = op2 + ml;
             }
@@ -154,7 +154,7 @@ done:
 // kernel also knows how many source bytes are readable (`avail`) and reports -1 instead of reading
 // past them — the only deviation, and only on malformed input.
 template <int WARPS>
-__global__ void __launch_bounds__(WARPS * 32)
+__global__ void __launch_bounds__(WARPS * 32, 2048 / (WARPS * 32))
 lz4_decompress_fast_kernel(const uint8_t* __restrict__ src_base, const uint64_t* __restrict__ src_off,
                            const int32_t* __restrict__ src_avail,
                            uint8_t* dst_base, const uint64_t* __restrict__ dst_off,
@@ -185,7 +185,7 @@ lz4_decompress_fast_kernel(const uint8_t* __restrict__ src_base, const uint64_t*
                 const uint32_t off = (uint32_t)src[ipo] | ((uint32_t)src[ipo + 1] << 8);
                 if (off > (uint32_t)op2 || off == 0) break;
                 __syncwarp();
-                if (off >= (uint32_t)ml) { if (lane < ml) dl[op2] = dl[op2 - (int)off]; }
+                if (off >= (uint32_t)ml) { if (lane < ml) dl[op2] = load_u8_l2(dl + op2 - (int)off); }
                 else warp_match_copy(dst + op2, (int)off, ml, lane);
                 ip = ipo + 2; op = op2 + ml;
             }
