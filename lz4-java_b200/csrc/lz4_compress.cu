@@ -34,19 +34,11 @@ struct InGlobal {
     const uint8_t* __restrict__ p;
     __device__ __forceinline__ uint32_t ld1(int i) const { return p[i]; }
     __device__ __forceinline__ uint32_t ld4(int i) const { return load_u32_unaligned(p + i); }
-    // "far" loads: random look-backs at candidate positions.  They bypass L1 (ld.global.cg) so that
-    // 32 scattered lines per step do not evict the forward stream, which L1 is kept for.
-    __device__ __forceinline__ uint32_t ld1_far(int i) const {
-        uint32_t v; asm volatile("ld.global.cg.u8 %0, [%1];" : "=r"(v) : "l"(p + i)); return v;
-    }
-    __device__ __forceinline__ uint32_t ld4_far(int i) const {
-        const uintptr_t a = reinterpret_cast<uintptr_t>(p + i);
-        const uint32_t sh = (uint32_t(a) & 3u) * 8u;
-        uint32_t lo, hi = 0;
-        asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(lo) : "l"(a & ~uintptr_t(3)));
-        if (sh) asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(hi) : "l"((a & ~uintptr_t(3)) + 4));
-        return __funnelshift_r(lo, hi, sh);
-    }
+    // "far" loads = look-backs at candidate positions.  Tried ld.global.cg (bypass L1) for these in
+    // round 1: L1 hit rate fell from 44% to 11% and throughput dropped (hl12: 69 -> 59 GiB/s), because the
+    // candidate line is re-read by the extension step; they stay on the default cached path.
+    __device__ __forceinline__ uint32_t ld1_far(int i) const { return ld1(i); }
+    __device__ __forceinline__ uint32_t ld4_far(int i) const { return ld4(i); }
     __device__ __forceinline__ const uint8_t* ptr(int i) const { return p + i; }
 };
 struct InShared {

@@ -77,7 +77,7 @@ lz4_decompress_safe_kernel(const uint8_t* __restrict__ src_base, const uint64_t*
                 const int op2 = op + (int)lit, ml = (int)mlc + 4;
                 if (op2 + ml >= oend - 64 || off > (uint32_t)op2 || off == 0) break;
                 __syncwarp();
-                if (off >= (uint32_t)ml) { if (lane < ml) dl[op2] = load_u8_l2(dl + op2 - (int)off); }
+                if (off >= (uint32_t)ml) { if (lane < ml) dl[op2] = dl[op2 - (int)off]; }
                 else warp_match_copy(dst + op2, (int)off, ml, lane);
                 ip = ipo + 2; op = op2 + ml;
             }
@@ -185,7 +185,7 @@ lz4_decompress_fast_kernel(const uint8_t* __restrict__ src_base, const uint64_t*
                 const uint32_t off = (uint32_t)src[ipo] | ((uint32_t)src[ipo + 1] << 8);
                 if (off > (uint32_t)op2 || off == 0) break;
                 __syncwarp();
-                if (off >= (uint32_t)ml) { if (lane < ml) dl[op2] = load_u8_l2(dl + op2 - (int)off); }
+                if (off >= (uint32_t)ml) { if (lane < ml) dl[op2] = dl[op2 - (int)off]; }
                 else warp_match_copy(dst + op2, (int)off, ml, lane);
                 ip = ipo + 2; op = op2 + ml;
             }

@@ -1,0 +1,71 @@
+"""C-ABI checks that need no GPU: the library loads, exports every symbol include/b200lz4.h declares,
+pure-arithmetic entry points work, and compute entry points fail LOUDLY (no CPU fallback) without a device."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    txt = open(os.path.join(ROOT, "include", "b200lz4.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200(?:lz4|xxh(?:32|64))_?\w*)\s*\(", txt)))
+
+
+def test_every_header_symbol_is_exported_and_bound(b200):
+    lib = b200._native.lib()
+    names = header_functions()
+    assert len(names) >= 35
+    bound = {n for n, _, _ in b200._native.SYMBOLS}
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/b200lz4.h but not exported"
+        assert n in bound, f"{n} exported but not bound in _native.SYMBOLS"
+    assert lib.b200lz4_version() == 100
+
+
+def test_compress_bound_matches_reference_formula(b200, port):
+    lib = b200._native.lib()
+    rng = np.random.default_rng(1)
+    for n in [0, 1, 254, 255, 256, 65536, 0x7E000000, 0x7E000001, -1] + [int(x) for x in rng.integers(0, 1 << 30, 50)]:
+        assert lib.b200lz4_compressBound(n) == port.compress_bound(n)
+    # LZ4Utils.maxCompressedLength == LZ4_compressBound for valid lengths (LZ4Test.java:80-87)
+    for n in (0, 1, 65536, 1 << 30):
+        assert b200.max_compressed_length(n) == port.compress_bound(n)
+    with pytest.raises(ValueError):
+        b200.max_compressed_length(-1)
+    with pytest.raises(ValueError):
+        b200.max_compressed_length(0x7E000000)
+
+
+def _no_gpu(b200):
+    return b200._native.lib().b200lz4_device_count() < 0
+
+
+def test_no_device_is_loud(b200):
+    """without a usable GPU the product raises; it never computes on the CPU"""
+    if not _no_gpu(b200):
+        pytest.skip("a CUDA device is present")
+    lib = b200._native.lib()
+    src = np.zeros(100, dtype=np.uint8)
+    dst = np.zeros(200, dtype=np.uint8)
+    assert lib.b200lz4_compress_default(src.ctypes.data, dst.ctypes.data, 100, 200) == b200._native.E_NODEVICE
+    assert "cuda" in b200._native.last_error().lower()
+    with pytest.raises(b200.B200Error):
+        b200.LZ4Factory.b200Instance()
+    with pytest.raises(b200.B200Error):
+        b200.batch.xxh32_batch_host(src, [0], [100])
+    with pytest.raises(b200.B200Error):
+        b200.XXHashFactory.b200Instance()
+
+
+def test_product_does_not_import_oracle():
+    """the package may not reference oracle/ in any way (checker is test infrastructure only)"""
+    pkg = os.path.join(ROOT, "lz4-java_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".java")):
+                txt = open(os.path.join(dp, f), errors="ignore").read()
+                assert "oracle" not in txt.lower().replace("test oracle", ""), os.path.join(dp, f)

@@ -1,0 +1,121 @@
+"""Pins the CPU oracle (oracle/*.c restatements) to the reference: against the committed golden
+vectors produced by the reference's own C (tests/golden/kat.json, always), and against
+oracle/_ref directly when it is available.  CPU only."""
+import hashlib
+import json
+import os
+import random
+
+import numpy as np
+import pytest
+
+import corpus
+
+KAT = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "kat.json")))
+
+
+def sha(b):
+    return hashlib.sha256(bytes(b)).hexdigest()
+
+
+def test_golden_datagen(port):
+    for e in KAT["datagen"]:
+        assert sha(port.datagen(e["size"], e["match_proba"], 0.0, e["seed"])) == e["sha256"], e
+
+
+def test_golden_xxhash(port):
+    stream = port.datagen(200000, 0.5, 0.0, 77).tobytes()
+    for e in KAT["xxh"]:
+        buf = stream[: e["len"]]
+        assert port.xxh32(buf, e["seed"]) == e["xxh32"], e
+        assert port.xxh64(buf, e["seed"] * 0x100000001) == e["xxh64"], e
+    # python-xxhash (libxxhash 0.8) as an independent second witness
+    xx = pytest.importorskip("xxhash")
+    for n in (0, 5, 17, 4096, 100001):
+        assert port.xxh32(stream[:n], 7) == xx.xxh32_intdigest(stream[:n], 7)
+        assert port.xxh64(stream[:n], 7) == xx.xxh64_intdigest(stream[:n], 7)
+
+
+def test_golden_xxhash_streaming(port):
+    rng = random.Random(3)
+    stream = port.datagen(200000, 0.5, 0.0, 77).tobytes()
+    for e in KAT["xxh"][::3]:
+        buf = stream[: e["len"]]
+        cuts = sorted(rng.randint(0, len(buf)) for _ in range(4))
+        chunks = [buf[a:b] for a, b in zip([0] + cuts, cuts + [len(buf)])]
+        assert port.xxh_stream(32, chunks, e["seed"]) == e["xxh32"]
+        assert port.xxh_stream(64, chunks, e["seed"] * 0x100000001) == e["xxh64"]
+
+
+def test_golden_compress_bytes_and_roundtrip(port):
+    """the restated compressor reproduces the reference's exact bytes (so ratio comparisons are
+    against the reference's own parse), and both restated decoders invert it"""
+    by_name = {e["name"]: e for e in KAT["compress"]}
+    for name, d in corpus.blocks(port):
+        e = by_name[name]
+        assert sha(d) == e["in_sha256"], name
+        c = port.compress(d)
+        assert len(c) == e["clen"] and sha(c) == e["c_sha256"], name
+        r, out = port.decompress_safe(c, len(d))
+        assert r == len(d) and out == d, name
+        r, out = port.decompress_fast(c, len(d))
+        assert r == len(c) and out == d, name
+
+
+def test_golden_malformed_codes(port):
+    for e in KAT["malformed_safe"]:
+        assert port.decompress_safe(bytes.fromhex(e["hex"]), e["cap"])[0] == e["ret"], e
+    for e in KAT["malformed_fast"]:
+        assert port.decompress_fast(bytes.fromhex(e["hex"]), e["n"])[0] == e["ret"], e
+
+
+def test_compress_bound(port):
+    assert port.compress_bound(65536) == 65809 and port.compress_bound(0) == 16
+    assert port.compress_bound(0x7E000000) == 0x7E000000 + 0x7E000000 // 255 + 16
+    assert port.compress_bound(0x7E000001) == 0 and port.compress_bound(-1) == 0
+
+
+# ------------------------------------------------------------------ differential against oracle/_ref
+def test_ref_differential_codec(port, ref):
+    assert ref.version() == KAT["lz4_version"]
+    rng = random.Random(2)
+    bad = 0
+    for name, d in corpus.blocks(ref, big=False) + corpus.calgary_blocks(2):
+        c = ref.compress(d)
+        assert port.compress(d) == c, name
+        for cap in (len(c) - 1, len(c), len(c) + 3, len(c) // 2):
+            assert port.compress(d, cap) == ref.compress(d, cap), (name, cap)     # limitedOutput thresholds
+        n = len(d)
+        variants = [(c, n), (c, n - 1), (c, n + 1), (c, n + 64), (c, 0), (c[:-1], n), (c + b"\0", n)]
+        variants += [(m, rng.choice([n, n + 1, n + 70, max(0, n - 5)])) for m in corpus.mutate(c, rng, 25)]
+        for cc, cap in variants:
+            if not cc:
+                continue
+            a, b = port.decompress_safe(cc, cap), ref.decompress_safe(cc, cap)
+            bad += a != b
+            if cap >= 0:
+                a, b = port.decompress_fast(cc, cap), ref.decompress_fast(cc, cap)
+                bad += (a[0] != b[0]) or (b[0] >= 0 and a[1] != b[1])
+    assert bad == 0
+
+
+def test_ref_differential_frames(port, ref):
+    """frames written by the restatement decode with the reference's LZ4F_decompress and vice versa"""
+    for n in (0, 1, 100, 65536, 65537, 300000, 5 << 20):
+        data = ref.datagen(n, 0.5, 0.0, n & 0xFF).tobytes()
+        for bs in (4, 7):
+            for flags in (0, 1, 3, 5, 7):
+                f = port.frame_compress(data, bs, flags)
+                r, out = ref.frame_decompress(f, n + 16)
+                assert r == n and out == data, (n, bs, flags)
+                g = ref.frame_compress(data, bs, flags)
+                r, out = port.frame_decompress(g, n + 16)
+                assert r == n and out == data, (n, bs, flags, r)
+    # concatenated + skippable frames (LZ4FrameIOStreamTest.java:253-309, 378-426)
+    a, b = b"hello frame " * 1000, ref.datagen(70000, 0.5, 0.0, 1).tobytes()
+    skip = bytes([0x50, 0x2A, 0x4D, 0x18, 4, 0, 0, 0, 1, 2, 3, 4])
+    cat = port.frame_compress(a, 4, 1) + skip + ref.frame_compress(b, 5, 1)
+    r, out = port.frame_decompress(cat, len(a) + len(b))
+    assert r == len(a) + len(b) and out == a + b
+    bad = bytearray(port.frame_compress(b, 4, 1)); bad[-1] ^= 1          # content checksum mismatch
+    assert port.frame_decompress(bytes(bad), len(b))[0] == -7
