@@ -1,0 +1,50 @@
+package net.jpountz.lz4;
+
+import java.nio.ByteBuffer;
+import java.nio.ByteOrder;
+import java.nio.IntBuffer;
+import java.nio.LongBuffer;
+
+/**
+ * Batch API of the B200 backend: n independent blocks per call over DIRECT ByteBuffers
+ * (register them once with {@link #pin(ByteBuffer)} so the device DMAs straight from/to them).
+ * This is what makes a GPU backend worthwhile: the per-block {@code LZ4Compressor.compress} API
+ * pays one launch and two PCIe round trips for 64 KiB (SURVEY.md §7).
+ */
+public final class LZ4B200Batch {
+  private LZ4B200Batch() {}
+
+  public static void pin(ByteBuffer direct) {
+    if (!direct.isDirect()) throw new IllegalArgumentException("direct buffer required");
+    if (LZ4B200JNI.registerDirectBuffer(direct) != 0) throw new LZ4Exception("cudaHostRegister failed");
+  }
+
+  static LongBuffer longs(int n) { return ByteBuffer.allocateDirect(8 * n).order(ByteOrder.nativeOrder()).asLongBuffer(); }
+  static IntBuffer ints(int n) { return ByteBuffer.allocateDirect(4 * n).order(ByteOrder.nativeOrder()).asIntBuffer(); }
+
+  /** Compresses n equally sized blocks laid out back to back in src into bound-sized slots of dst; returns per-block sizes. */
+  public static int[] compressUniform(ByteBuffer src, int blockSize, int n, ByteBuffer dst) {
+    final int bound = LZ4Utils.maxCompressedLength(blockSize);
+    final LongBuffer so = longs(n), dof = longs(n);
+    final IntBuffer sl = ints(n), dc = ints(n), res = ints(n);
+    for (int i = 0; i < n; i++) { so.put(i, (long) i * blockSize); sl.put(i, blockSize); dof.put(i, (long) i * bound); dc.put(i, bound); }
+    final int rc = LZ4B200JNI.compressBatch(src, so, sl, dst, dof, dc, res, n, blockSize);
+    if (rc != 0) throw new LZ4Exception("B200 backend error " + rc);
+    final int[] out = new int[n];
+    res.get(out);
+    for (int r : out) if (r <= 0) throw new LZ4Exception("maxDestLen is too small");
+    return out;
+  }
+
+  /** Inverse of {@link #compressUniform}: fast-decompresses n slots into blockSize-byte blocks. */
+  public static void decompressUniform(ByteBuffer src, int[] compressedLen, int blockSize, ByteBuffer dst) {
+    final int n = compressedLen.length;
+    final int bound = LZ4Utils.maxCompressedLength(blockSize);
+    final LongBuffer so = longs(n), dof = longs(n);
+    final IntBuffer sa = ints(n), dl = ints(n), res = ints(n);
+    for (int i = 0; i < n; i++) { so.put(i, (long) i * bound); sa.put(i, bound); dof.put(i, (long) i * blockSize); dl.put(i, blockSize); }
+    final int rc = LZ4B200JNI.decompressFastBatch(src, so, sa, dst, dof, dl, res, n);
+    if (rc != 0) throw new LZ4Exception("B200 backend error " + rc);
+    for (int i = 0; i < n; i++) if (res.get(i) != compressedLen[i]) throw new LZ4Exception("Error decoding block " + i);
+  }
+}

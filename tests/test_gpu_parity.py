@@ -290,3 +290,59 @@ def test_factory_api_contract(b200, checker):
         with pytest.raises(b200.LZ4Exception):
             safe.decompress(v, 0, len(v), bytearray(64), 0, 64)
     safe.decompress(corpus.MALFORMED[0], 0, len(corpus.MALFORMED[0]), bytearray(64), 0, 64)   # must not throw or hang
+
+
+def test_jni_shim_through_fake_jnienv(b200, checker, tmp_path):
+    """lz4-java_b200/jni/b200_jni.c compiled against tests/jni_fake/jni.h (no JDK here) and driven from C:
+    byte[] / direct-buffer operands with offsets, return conventions, balanced critical sections."""
+    import os
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "jni_harness")
+    pkg = os.path.join(root, "lz4-java_b200")
+    subprocess.run(["gcc", "-O1", "-I" + os.path.join(root, "tests", "jni_fake"), "-I" + os.path.join(root, "include"),
+                    os.path.join(root, "tests", "jni_fake", "harness.c"), os.path.join(pkg, "jni", "b200_jni.c"),
+                    "-L" + pkg, "-lb200lz4", "-Wl,-rpath," + pkg, "-o", exe], check=True)
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0 and out.stdout.startswith("ok"), out.stdout + out.stderr
+    # the hashes printed by the harness must be the oracle's for the same generated bytes
+    raw = bytearray(20007)
+    s = 1
+    for i in range(len(raw)):
+        s = (s * 1103515245 + 12345) & 0xFFFFFFFF
+        raw[i] = (i % 13) if (i % 97 < 60) else (s >> 24)
+    m = re.search(r"xxh64=([0-9a-f]+) xxh32=([0-9a-f]+)", out.stdout)
+    assert int(m.group(1), 16) == checker.xxh64(bytes(raw[7:]), 42)
+    assert int(m.group(2), 16) == checker.xxh32(bytes(raw[7:]), 7)
+
+
+def test_hc_compress_roundtrip_and_ratio(b200, checker):
+    """LZ4 HC (level 9 class): valid stream, never worse than the fast parse, close to the reference's HC-9"""
+    items = [(nm, d) for nm, d in corpus.blocks(checker) if len(d) in (0, 1, 12, 13, 64, 1000, 4096, 65536) or nm.startswith("period")]
+    items += [(f"rdg256k_{mp}", checker.datagen(262144, mp, 0.0, 4).tobytes()) for mp in (0.2, 0.5, 0.8)]
+    items += corpus.calgary_blocks(2)
+    src, soff, slen = corpus.pack([d for _, d in items])
+    bounds = [b200.max_compressed_length(len(d)) for _, d in items]
+    doff, dcap, total = _slots(bounds)
+    dst = np.zeros(total, dtype=np.uint8)
+    res = b200.batch.compress_hc_batch_host(src, soff, slen, dst, doff, dcap, level=9)
+    fast = b200.batch.compress_fast_batch_host(src, soff, slen, np.zeros(total, dtype=np.uint8), doff, dcap, max_src_len=0)
+    tot = tot_fast = tot_ref = 0
+    for k, (name, d) in enumerate(items):
+        assert 0 < res[k] <= bounds[k], (name, int(res[k]))
+        c = dst[int(doff[k]):int(doff[k]) + int(res[k])].tobytes()
+        r, out = checker.decompress_safe(c, len(d))
+        assert r == len(d) and out == d, name
+        tot += len(c); tot_fast += int(fast[k])
+        if hasattr(checker, "compress_hc"):
+            tot_ref += len(checker.compress_hc(d, 9))
+    assert tot <= tot_fast, (tot, tot_fast)
+    if tot_ref:
+        assert tot < 1.08 * tot_ref, (tot, tot_ref)
+    # the single-block entry point the JNI shim binds, and level clamping of the factory (LZ4Factory.java:263-270)
+    F = b200.LZ4Factory.b200Instance()
+    d = items[-1][1]
+    for lvl in (-5, 1, 9, 17, 99):
+        c = F.highCompressor(lvl).compress(d)
+        assert checker.decompress_safe(c, len(d))[1] == d
