@@ -141,6 +141,21 @@ int b200lz4_compress_fast_compact_host(const uint8_t* src_base, const uint64_t* 
                                        uint8_t* dst_base, size_t dst_capacity, uint64_t* out_off,
                                        int32_t* result, size_t n, int max_src_len, uint64_t* total);
 
+/* ---------------------------------------------------------------- LZ4 Frame batch decoder
+ * LZ4FrameInputStream semantics (src/java/net/jpountz/lz4/LZ4FrameInputStream.java:132-321) over a buffer
+ * of concatenated frames: the host indexes the container, the device verifies header/block/content
+ * XXH32 checksums and decodes all blocks of all frames in batched launches.
+ * Error codes (negative): -1 premature end, -2 bad magic, -3 descriptor checksum, -4 block larger than the
+ * frame's maximum, -5 block checksum, -6 block decode error, -7 content checksum, -8 content size,
+ * -9 dst too small, -10 unsupported descriptor, -11 (decode_dev only) a short block in mid-frame. */
+int64_t b200lz4f_decompress_host(const uint8_t* src, size_t srcSize, uint8_t* dst, size_t dstCapacity);
+void*   b200lz4f_index_create(const uint8_t* src_host, size_t srcSize, uint64_t* slot_bytes, int* err);
+size_t  b200lz4f_index_frames(void* index);
+size_t  b200lz4f_index_blocks(void* index);
+int64_t b200lz4f_decode_dev(void* index, const uint8_t* d_src, uint8_t* d_slots, uint64_t* frame_off, uint64_t* frame_len,
+                            int32_t* block_len_out, void* stream);
+void    b200lz4f_index_free(void* index);
+
 /* kernel-launch counter (bench.py's "gpu_launches"): number of kernels this library has
  * launched from the calling process since load / since the last reset. */
 uint64_t b200lz4_launch_count(void);

@@ -9,7 +9,9 @@ from .lz4 import (LZ4Factory, LZ4Compressor, LZ4FastDecompressor, LZ4SafeDecompr
                   max_compressed_length)
 from .xxhash import XXHashFactory, XXHash32, XXHash64, StreamingXXHash32, StreamingXXHash64
 from . import batch
+from . import frame
+from .frame import decompress_frames, LZ4FrameError
 
 __all__ = ["LZ4Factory", "LZ4Compressor", "LZ4FastDecompressor", "LZ4SafeDecompressor", "LZ4Exception",
            "XXHashFactory", "XXHash32", "XXHash64", "StreamingXXHash32", "StreamingXXHash64",
-           "max_compressed_length", "batch", "B200Error"]
+           "max_compressed_length", "batch", "B200Error", "frame", "decompress_frames", "LZ4FrameError"]

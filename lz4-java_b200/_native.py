@@ -51,6 +51,12 @@ SYMBOLS = [
     ("b200xxh32_batch_host", _i, [_vp, _vp, _vp, _u32, _vp, _sz]),
     ("b200xxh64_batch_host", _i, [_vp, _vp, _vp, _u64, _vp, _sz]),
     ("b200lz4_compress_fast_compact_host", _i, [_vp, _vp, _vp, _vp, _sz, _vp, _vp, _sz, _i, _vp]),
+    ("b200lz4f_decompress_host", C.c_int64, [_vp, _sz, _vp, _sz]),
+    ("b200lz4f_index_create", _vp, [_vp, _sz, _vp, _vp]),
+    ("b200lz4f_index_frames", _sz, [_vp]),
+    ("b200lz4f_index_blocks", _sz, [_vp]),
+    ("b200lz4f_decode_dev", C.c_int64, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    ("b200lz4f_index_free", None, [_vp]),
     ("b200lz4_launch_count", _u64, []),
     ("b200lz4_launch_count_reset", None, []),
 ]

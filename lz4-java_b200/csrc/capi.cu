@@ -16,6 +16,7 @@
 namespace b200 {
 
 static std::atomic<unsigned long long> g_launches{0};
+unsigned long long g_launch_count = 0;      // launches made by frame.cu (single-threaded per call)
 static thread_local char tl_err[256] = "";
 static thread_local int tl_device = -1;          // -1: not chosen yet (defaults to device 0)
 
@@ -607,7 +608,7 @@ int b200lz4_compress_fast_compact_host(const uint8_t* src_base, const uint64_t* 
     return 0;
 }
 
-uint64_t b200lz4_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
-void     b200lz4_launch_count_reset(void) { g_launches.store(0, std::memory_order_relaxed); }
+uint64_t b200lz4_launch_count(void) { return g_launches.load(std::memory_order_relaxed) + g_launch_count; }
+void     b200lz4_launch_count_reset(void) { g_launches.store(0, std::memory_order_relaxed); g_launch_count = 0; }
 
 } // extern "C"

@@ -58,4 +58,12 @@ cudaError_t launch_compact(const uint8_t* slots, const uint64_t* slot_off, const
     return cudaGetLastError();
 }
 
+cudaError_t launch_gather(const uint8_t* src, const uint64_t* src_off, const int32_t* lens,
+                          uint8_t* dst, const uint64_t* dst_off, size_t n, cudaStream_t st)
+{
+    if (n == 0) return cudaSuccess;
+    compact_gather_kernel<<<(unsigned)((n + 3) / 4), 128, 0, st>>>(src, src_off, lens, dst, dst_off, (uint32_t)n);
+    return cudaGetLastError();
+}
+
 } // namespace b200

@@ -1,0 +1,324 @@
+// frame.cu — LZ4 Frame batch decoder: LZ4FrameInputStream semantics (reference:
+// src/java/net/jpountz/lz4/LZ4FrameInputStream.java:132-321; format src/lz4/doc/lz4_Frame_format.md)
+// for a buffer holding any number of concatenated frames (skippable frames included).
+//
+// The stream adapter in the reference is strictly sequential: one block in flight, one XXH32 state per
+// frame.  Here the host only INDEXES the container (magic / FLG / BD / block sizes: O(#blocks), no
+// payload byte is touched), and the payload work is three batched launches on the device:
+//   1. XXH32 over every frame descriptor (header checksum byte) and, if present, every block payload
+//      (block checksums)                                            -> xxh_batch_kernel<32>
+//   2. safe-decompress of every compressed block into its slot; stored blocks are copied
+//                                                                   -> lz4_decompress_safe_kernel, gather
+//   3. XXH32 over every frame's decoded content (content checksum)  -> xxh_batch_kernel<32>
+// Blocks of one frame are decoded in parallel because lz4-java only writes independent blocks
+// (LZ4FrameOutputStream.java:58,361-363; dependent blocks are rejected like the reference does).
+#include "../../include/b200lz4.h"
+#include "kernels.h"
+#include <cstring>
+#include <new>
+#include <vector>
+
+namespace b200 {
+
+cudaError_t launch_gather(const uint8_t* src, const uint64_t* src_off, const int32_t* lens,
+                          uint8_t* dst, const uint64_t* dst_off, size_t n, cudaStream_t st);
+
+static inline uint32_t rd32(const uint8_t* p) { return p[0] | (p[1] << 8) | (p[2] << 16) | ((uint32_t)p[3] << 24); }
+
+struct FrameRec {
+    uint64_t desc_off; int32_t desc_len; uint8_t hc_byte; uint8_t flg; uint32_t bs;
+    uint64_t content_size; bool has_size;
+    size_t first_block, nblocks;
+    uint32_t content_checksum; bool has_checksum;
+    uint64_t out_off;                   // slot-layout start of this frame's content
+};
+struct BlockRec { uint64_t src_off; uint32_t size; bool raw; uint32_t checksum; bool has_checksum; size_t frame; uint64_t out_off; };
+
+struct FrameIndex {
+    std::vector<FrameRec> frames;
+    std::vector<BlockRec> blocks;
+    uint64_t slot_bytes = 0;            // device bytes needed for the slot layout (upper bound of the decoded size)
+    // device-side descriptor arrays, built once
+    int device = -1;
+    uint8_t* d_blob = nullptr; size_t blob_bytes = 0;
+    std::vector<uint8_t> h_blob;
+    // offsets inside the blob
+    size_t o_c_soff, o_c_doff, o_c_slen, o_c_dcap, o_c_res;          // compressed blocks
+    size_t o_r_soff, o_r_doff, o_r_len;                              // raw blocks
+    size_t o_h_off, o_h_len, o_h_out;                                // header descriptors
+    size_t o_b_off, o_b_len, o_b_out;                                // block checksums
+    size_t o_f_off, o_f_len, o_f_out;                                // content checksums
+    size_t n_comp = 0, n_raw = 0, n_bsum = 0, n_fsum = 0;
+    std::vector<size_t> comp_ix, raw_ix, bsum_ix, fsum_ix;
+};
+
+// LZ4FrameInputStream.nextFrameInfo / readHeader / readBlock as a pure index pass
+static int index_frames(const uint8_t* src, size_t n, FrameIndex& ix)
+{
+    size_t ip = 0; bool seen = false;
+    while (ip < n) {
+        if (n - ip < 4) return -1;
+        const uint32_t magic = rd32(src + ip); ip += 4;
+        if ((magic >> 4) == (0x184D2A50u >> 4)) {                               // skippable (:154,162-173)
+            if (n - ip < 4) return -1;
+            const uint32_t sz = rd32(src + ip); ip += 4;
+            if (n - ip < sz) return -1;
+            ip += sz; seen = true; continue;
+        }
+        if (magic != 0x184D2204u) return -2;                                    // (:151)
+        FrameRec f{};
+        f.desc_off = ip;
+        if (n - ip < 3) return -1;
+        f.flg = src[ip++]; const uint8_t bd = src[ip++];
+        if ((f.flg >> 6) != 1 || (f.flg & 2) || !(f.flg & 0x20) || (f.flg & 1)) return -10;   // version, reserved, B.Indep, dictID
+        if ((bd & 0x8F) || (bd >> 4) < 4) return -10;
+        f.bs = 1u << (8 + 2 * (bd >> 4));
+        f.has_size = f.flg & 8;
+        if (f.has_size) { if (n - ip < 9) return -1; f.content_size = (uint64_t)rd32(src + ip) | ((uint64_t)rd32(src + ip + 4) << 32); ip += 8; }
+        if (n - ip < 1) return -1;
+        f.desc_len = (int32_t)(ip - f.desc_off);
+        f.hc_byte = src[ip++];
+        f.first_block = ix.blocks.size();
+        f.out_off = ix.slot_bytes;
+        for (;;) {                                                              // readBlock (:258-321)
+            if (n - ip < 4) return -1;
+            const uint32_t word = rd32(src + ip); ip += 4;
+            const uint32_t sz = word & 0x7FFFFFFFu;
+            if (sz == 0) break;                                                 // EndMark
+            if (sz > f.bs) return -4;
+            BlockRec b{}; b.src_off = ip; b.size = sz; b.raw = word >> 31; b.frame = ix.frames.size();
+            if (n - ip < sz) return -1;
+            ip += sz;
+            b.has_checksum = f.flg & 0x10;
+            if (b.has_checksum) { if (n - ip < 4) return -1; b.checksum = rd32(src + ip); ip += 4; }
+            b.out_off = ix.slot_bytes; ix.slot_bytes += f.bs;
+            ix.blocks.push_back(b);
+        }
+        f.nblocks = ix.blocks.size() - f.first_block;
+        f.has_checksum = f.flg & 4;
+        if (f.has_checksum) { if (n - ip < 4) return -1; f.content_checksum = rd32(src + ip); ip += 4; }
+        ix.frames.push_back(f); seen = true;
+    }
+    return seen ? 0 : -1;
+}
+
+template <typename T> static size_t put(std::vector<uint8_t>& blob, size_t count)
+{
+    size_t o = (blob.size() + 15) & ~size_t(15);
+    blob.resize(o + count * sizeof(T));
+    return o;
+}
+
+static int build_descriptors(FrameIndex& ix)
+{
+    for (size_t i = 0; i < ix.blocks.size(); i++) {
+        (ix.blocks[i].raw ? ix.raw_ix : ix.comp_ix).push_back(i);
+        if (ix.blocks[i].has_checksum) ix.bsum_ix.push_back(i);
+    }
+    for (size_t f = 0; f < ix.frames.size(); f++) if (ix.frames[f].has_checksum) ix.fsum_ix.push_back(f);
+    ix.n_comp = ix.comp_ix.size(); ix.n_raw = ix.raw_ix.size(); ix.n_bsum = ix.bsum_ix.size(); ix.n_fsum = ix.fsum_ix.size();
+    auto& B = ix.h_blob;
+    const size_t nf = ix.frames.size();
+    ix.o_c_soff = put<uint64_t>(B, ix.n_comp); ix.o_c_doff = put<uint64_t>(B, ix.n_comp);
+    ix.o_c_slen = put<int32_t>(B, ix.n_comp);  ix.o_c_dcap = put<int32_t>(B, ix.n_comp); ix.o_c_res = put<int32_t>(B, ix.n_comp);
+    ix.o_r_soff = put<uint64_t>(B, ix.n_raw);  ix.o_r_doff = put<uint64_t>(B, ix.n_raw); ix.o_r_len = put<int32_t>(B, ix.n_raw);
+    ix.o_h_off = put<uint64_t>(B, nf); ix.o_h_len = put<int32_t>(B, nf); ix.o_h_out = put<uint32_t>(B, nf);
+    ix.o_b_off = put<uint64_t>(B, ix.n_bsum); ix.o_b_len = put<int32_t>(B, ix.n_bsum); ix.o_b_out = put<uint32_t>(B, ix.n_bsum);
+    ix.o_f_off = put<uint64_t>(B, ix.n_fsum); ix.o_f_len = put<int32_t>(B, ix.n_fsum); ix.o_f_out = put<uint32_t>(B, ix.n_fsum);
+    B.resize((B.size() + 15) & ~size_t(15));
+    uint8_t* p = B.data();
+    for (size_t k = 0; k < ix.n_comp; k++) {
+        const BlockRec& b = ix.blocks[ix.comp_ix[k]];
+        ((uint64_t*)(p + ix.o_c_soff))[k] = b.src_off; ((uint64_t*)(p + ix.o_c_doff))[k] = b.out_off;
+        ((int32_t*)(p + ix.o_c_slen))[k] = (int32_t)b.size; ((int32_t*)(p + ix.o_c_dcap))[k] = (int32_t)ix.frames[b.frame].bs;
+    }
+    for (size_t k = 0; k < ix.n_raw; k++) {
+        const BlockRec& b = ix.blocks[ix.raw_ix[k]];
+        ((uint64_t*)(p + ix.o_r_soff))[k] = b.src_off; ((uint64_t*)(p + ix.o_r_doff))[k] = b.out_off; ((int32_t*)(p + ix.o_r_len))[k] = (int32_t)b.size;
+    }
+    for (size_t f = 0; f < nf; f++) { ((uint64_t*)(p + ix.o_h_off))[f] = ix.frames[f].desc_off; ((int32_t*)(p + ix.o_h_len))[f] = ix.frames[f].desc_len; }
+    for (size_t k = 0; k < ix.n_bsum; k++) {
+        const BlockRec& b = ix.blocks[ix.bsum_ix[k]];
+        ((uint64_t*)(p + ix.o_b_off))[k] = b.src_off; ((int32_t*)(p + ix.o_b_len))[k] = (int32_t)b.size;
+    }
+    return 0;
+}
+
+} // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+void* b200lz4f_index_create(const uint8_t* src_host, size_t n, uint64_t* slot_bytes, int* err)
+{
+    FrameIndex* ix = new (std::nothrow) FrameIndex();
+    if (!ix) { if (err) *err = B200LZ4_E_ARG; return nullptr; }
+    int rc = src_host ? index_frames(src_host, n, *ix) : -1;
+    if (rc == 0) rc = build_descriptors(*ix);
+    if (rc) { delete ix; if (err) *err = rc; return nullptr; }
+    if (slot_bytes) *slot_bytes = ix->slot_bytes;
+    if (err) *err = 0;
+    return ix;
+}
+
+void b200lz4f_index_free(void* index)
+{
+    FrameIndex* ix = (FrameIndex*)index;
+    if (!ix) return;
+    if (ix->d_blob) { cudaSetDevice(ix->device); cudaFree(ix->d_blob); }
+    delete ix;
+}
+
+// Decode every indexed frame: d_src holds the container bytes, d_slots (>= slot_bytes) receives block k
+// of frame f at frames[f].out_off + k*blockMaxSize.  On success frame_off[f] / frame_len[f] (host
+// arrays, may be NULL) describe each frame's content, contiguous inside d_slots when no block was
+// flushed short mid-frame (otherwise -11 is returned: caller should use the host path, which
+// stitches runs).  Returns total decoded bytes or a negative code.
+int64_t b200lz4f_decode_dev(void* index, const uint8_t* d_src, uint8_t* d_slots, uint64_t* frame_off, uint64_t* frame_len,
+                            int32_t* block_len_out, void* stream)
+{
+    FrameIndex& ix = *(FrameIndex*)index;
+    cudaStream_t st = (cudaStream_t)stream;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return B200LZ4_E_NODEVICE;
+    if (!ix.d_blob || ix.device != dev) {
+        if (ix.d_blob) { cudaSetDevice(ix.device); cudaFree(ix.d_blob); cudaSetDevice(dev); ix.d_blob = nullptr; }
+        if (cudaMalloc(&ix.d_blob, ix.h_blob.size() + 16) != cudaSuccess) return B200LZ4_E_CUDA;
+        ix.device = dev;
+    }
+    uint8_t* D = ix.d_blob; uint8_t* H = ix.h_blob.data();
+    const size_t nf = ix.frames.size();
+    if (cudaMemcpyAsync(D, H, ix.h_blob.size(), cudaMemcpyHostToDevice, st) != cudaSuccess) return B200LZ4_E_CUDA;
+    // 1. header + block checksums
+    g_launch_count += 1;
+    if (launch_xxh32(d_src, (uint64_t*)(D + ix.o_h_off), (int32_t*)(D + ix.o_h_len), 0, (uint32_t*)(D + ix.o_h_out), nf, st) != cudaSuccess) return B200LZ4_E_CUDA;
+    if (ix.n_bsum) {
+        g_launch_count += 1;
+        if (launch_xxh32(d_src, (uint64_t*)(D + ix.o_b_off), (int32_t*)(D + ix.o_b_len), 0, (uint32_t*)(D + ix.o_b_out), ix.n_bsum, st) != cudaSuccess) return B200LZ4_E_CUDA;
+    }
+    // 2. blocks
+    if (ix.n_comp) {
+        BatchArgs a{ d_src, (uint64_t*)(D + ix.o_c_soff), (int32_t*)(D + ix.o_c_slen), d_slots, (uint64_t*)(D + ix.o_c_doff),
+                     (int32_t*)(D + ix.o_c_dcap), (int32_t*)(D + ix.o_c_res), ix.n_comp };
+        g_launch_count += 1;
+        if (launch_decompress_safe(a, st) != cudaSuccess) return B200LZ4_E_CUDA;
+    }
+    if (ix.n_raw) {
+        g_launch_count += 1;
+        if (launch_gather(d_src, (uint64_t*)(D + ix.o_r_soff), (int32_t*)(D + ix.o_r_len), d_slots, (uint64_t*)(D + ix.o_r_doff), ix.n_raw, st) != cudaSuccess) return B200LZ4_E_CUDA;
+    }
+    // sizes come back; content-checksum descriptors depend on them
+    if (cudaMemcpyAsync(H + ix.o_c_res, D + ix.o_c_res, ix.n_comp * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) return B200LZ4_E_CUDA;
+    if (cudaMemcpyAsync(H + ix.o_h_out, D + ix.o_h_out, nf * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) return B200LZ4_E_CUDA;
+    if (ix.n_bsum && cudaMemcpyAsync(H + ix.o_b_out, D + ix.o_b_out, ix.n_bsum * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) return B200LZ4_E_CUDA;
+    if (cudaStreamSynchronize(st) != cudaSuccess) return B200LZ4_E_CUDA;
+
+    for (size_t f = 0; f < nf; f++)
+        if ((( ((uint32_t*)(H + ix.o_h_out))[f] >> 8) & 0xFF) != ix.frames[f].hc_byte) return -3;      // (:208-216)
+    for (size_t k = 0; k < ix.n_bsum; k++)
+        if (((uint32_t*)(H + ix.o_b_out))[k] != ix.blocks[ix.bsum_ix[k]].checksum) return -5;          // (:298-303)
+    std::vector<int32_t> blen(ix.blocks.size());
+    for (size_t k = 0; k < ix.n_comp; k++) {
+        const int32_t r = ((int32_t*)(H + ix.o_c_res))[k];
+        if (r < 0) return -6;                                                                           // LZ4Exception -> IOException (:307-311)
+        blen[ix.comp_ix[k]] = r;
+    }
+    for (size_t k = 0; k < ix.n_raw; k++) blen[ix.raw_ix[k]] = (int32_t)ix.blocks[ix.raw_ix[k]].size;
+    if (block_len_out) memcpy(block_len_out, blen.data(), blen.size() * sizeof(int32_t));
+    int64_t total = 0; bool gaps = false;
+    for (size_t f = 0; f < nf; f++) {
+        const FrameRec& fr = ix.frames[f];
+        uint64_t len = 0;
+        for (size_t k = 0; k < fr.nblocks; k++) {
+            const int32_t l = blen[fr.first_block + k];
+            if (k + 1 < fr.nblocks && (uint32_t)l != fr.bs) gaps = true;      // a short block in the middle of a frame
+            len += (uint64_t)l;
+        }
+        if (fr.has_size && fr.content_size != len) return -8;                                           // (:270-272)
+        if (frame_off) frame_off[f] = fr.out_off;
+        if (frame_len) frame_len[f] = len;
+        total += (int64_t)len;
+    }
+    if (gaps) return -11;
+    // 3. content checksums over each frame's (contiguous) content
+    if (ix.n_fsum) {
+        for (size_t k = 0; k < ix.n_fsum; k++) {
+            const FrameRec& fr = ix.frames[ix.fsum_ix[k]];
+            uint64_t len = 0; for (size_t j = 0; j < fr.nblocks; j++) len += (uint64_t)blen[fr.first_block + j];
+            if (len > 0x7FFFFFFFull) return -10;                              // one lane hashes one frame; >2 GiB frames are not indexed as one buffer
+            ((uint64_t*)(H + ix.o_f_off))[k] = fr.out_off; ((int32_t*)(H + ix.o_f_len))[k] = (int32_t)len;
+        }
+        if (cudaMemcpyAsync(D + ix.o_f_off, H + ix.o_f_off, ix.n_fsum * 8, cudaMemcpyHostToDevice, st) != cudaSuccess) return B200LZ4_E_CUDA;
+        if (cudaMemcpyAsync(D + ix.o_f_len, H + ix.o_f_len, ix.n_fsum * 4, cudaMemcpyHostToDevice, st) != cudaSuccess) return B200LZ4_E_CUDA;
+        g_launch_count += 1;
+        if (launch_xxh32(d_slots, (uint64_t*)(D + ix.o_f_off), (int32_t*)(D + ix.o_f_len), 0, (uint32_t*)(D + ix.o_f_out), ix.n_fsum, st) != cudaSuccess) return B200LZ4_E_CUDA;
+        if (cudaMemcpyAsync(H + ix.o_f_out, D + ix.o_f_out, ix.n_fsum * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) return B200LZ4_E_CUDA;
+        if (cudaStreamSynchronize(st) != cudaSuccess) return B200LZ4_E_CUDA;
+        for (size_t k = 0; k < ix.n_fsum; k++)
+            if (((uint32_t*)(H + ix.o_f_out))[k] != ix.frames[ix.fsum_ix[k]].content_checksum) return -7;   // (:266-269)
+    }
+    return total;
+}
+
+size_t b200lz4f_index_frames(void* index) { return ((FrameIndex*)index)->frames.size(); }
+size_t b200lz4f_index_blocks(void* index) { return ((FrameIndex*)index)->blocks.size(); }
+
+// Whole thing with HOST buffers: index, upload, decode, download frame by frame into one contiguous stream.
+int64_t b200lz4f_decompress_host(const uint8_t* src, size_t n, uint8_t* dst, size_t dst_capacity)
+{
+    int err = 0; uint64_t slot_bytes = 0;
+    void* index = b200lz4f_index_create(src, n, &slot_bytes, &err);
+    if (!index) return err;
+    FrameIndex& ix = *(FrameIndex*)index;
+    int64_t rc = 0;
+    uint8_t *d_src = nullptr, *d_slots = nullptr;
+    cudaStream_t st = nullptr;
+    std::vector<uint64_t> foff(ix.frames.size()), flen(ix.frames.size());
+    std::vector<int32_t> blen(ix.blocks.size());
+    do {
+        if (b200lz4_device_count() <= 0) { rc = B200LZ4_E_NODEVICE; break; }
+        if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaMalloc(&d_src, n + 16) != cudaSuccess || cudaMalloc(&d_slots, slot_bytes + 16) != cudaSuccess) { rc = B200LZ4_E_CUDA; break; }
+        if (cudaMemcpyAsync(d_src, src, n, cudaMemcpyHostToDevice, st) != cudaSuccess) { rc = B200LZ4_E_CUDA; break; }
+        rc = b200lz4f_decode_dev(index, d_src, d_slots, foff.data(), flen.data(), blen.data(), st);
+        if (rc < 0 && rc != -11) break;
+        // download: per frame when contiguous, else per run of blocks (short blocks in the middle of a frame)
+        uint64_t pos = 0; bool ok = true;
+        if (rc >= 0) {
+            for (size_t f = 0; f < ix.frames.size() && ok; f++) {
+                if (pos + flen[f] > dst_capacity) { rc = -9; ok = false; break; }
+                if (flen[f] && cudaMemcpyAsync(dst + pos, d_slots + foff[f], flen[f], cudaMemcpyDeviceToHost, st) != cudaSuccess) { rc = B200LZ4_E_CUDA; ok = false; }
+                pos += flen[f];
+            }
+        } else {
+            // general layout: copy block by block, then verify content checksums with a second pass over dst on the device
+            rc = 0;
+            for (size_t b = 0; b < ix.blocks.size() && ok; b++) {
+                const uint64_t l = (uint64_t)blen[b];
+                if (pos + l > dst_capacity) { rc = -9; ok = false; break; }
+                if (l && cudaMemcpyAsync(dst + pos, d_slots + ix.blocks[b].out_off, l, cudaMemcpyDeviceToHost, st) != cudaSuccess) { rc = B200LZ4_E_CUDA; ok = false; }
+                pos += l;
+            }
+            if (ok && cudaStreamSynchronize(st) != cudaSuccess) { rc = B200LZ4_E_CUDA; ok = false; }
+            if (ok) {
+                uint64_t p2 = 0;
+                for (size_t f = 0; f < ix.frames.size() && ok; f++) {
+                    if (ix.frames[f].has_checksum) {
+                        if (flen[f] > 0x7FFFFFFFull) { rc = -10; ok = false; break; }
+                        if (b200xxh32(dst + p2, (size_t)flen[f], 0) != ix.frames[f].content_checksum) { rc = -7; ok = false; }
+                    }
+                    p2 += flen[f];
+                }
+            }
+        }
+        if (ok) { if (cudaStreamSynchronize(st) != cudaSuccess) rc = B200LZ4_E_CUDA; else rc = (int64_t)pos; }
+    } while (0);
+    if (d_src) cudaFree(d_src);
+    if (d_slots) cudaFree(d_slots);
+    if (st) cudaStreamDestroy(st);
+    b200lz4f_index_free(index);
+    return rc;
+}
+
+} // extern "C"

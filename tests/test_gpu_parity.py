@@ -346,3 +346,45 @@ def test_hc_compress_roundtrip_and_ratio(b200, checker):
     for lvl in (-5, 1, 9, 17, 99):
         c = F.highCompressor(lvl).compress(d)
         assert checker.decompress_safe(c, len(d))[1] == d
+
+
+def test_frame_batch_decoder(b200, port):
+    """LZ4 Frame container (config 3's driver): frames written by the oracle (and by the reference's
+    LZ4F_compressFrame when available) decode bit-exactly; every checksum / truncation error of
+    LZ4FrameInputStream is reported with the oracle's code"""
+    from oracle import oracle as O
+    writers = [port]
+    try:
+        writers.append(O.Ref())
+    except (FileNotFoundError, OSError):
+        pass
+    rng = random.Random(4)
+    for w in writers:
+        for n in (0, 1, 100, 65536, 65537, 300000, 9 << 20):
+            data = port.datagen(n, 0.5, 0.0, n & 0xFF).tobytes() if n < (1 << 20) else (port.datagen(1 << 20, 0.5, 0.0, 3).tobytes() * 9)[:n]
+            for bs in (4, 5, 7):
+                for flags in (0, 1, 3, 5, 7):
+                    f = w.frame_compress(data, bs, flags)
+                    assert b200.decompress_frames(f, n + 8) == data, (w.kind, n, bs, flags)
+    # incompressible data -> stored (raw) blocks (LZ4FrameOutputStream.java:215-222)
+    noise = rng.randbytes(200000)
+    assert b200.decompress_frames(port.frame_compress(noise, 4, 3), len(noise)) == noise
+    # concatenated + skippable frames (LZ4FrameIOStreamTest.java:253-309, 378-426)
+    a, b = b"hello frame " * 1000, port.datagen(70000, 0.5, 0.0, 1).tobytes()
+    skip = bytes([0x50, 0x2A, 0x4D, 0x18, 4, 0, 0, 0, 1, 2, 3, 4])
+    cat = port.frame_compress(a, 4, 1) + skip + port.frame_compress(b, 5, 7) + port.frame_compress(b"", 4, 1)
+    assert b200.decompress_frames(cat, len(a) + len(b)) == a + b
+    # error parity with the oracle's codes
+    good = port.frame_compress(b, 4, 7)
+    cases = {"truncated": good[:-3], "truncated2": good[:20], "magic": b"\x01\x02\x03\x04" + good[4:],
+             "descriptor": good[:5] + bytes([good[5] ^ 0x10]) + good[6:], "content": good[:-1] + bytes([good[-1] ^ 1]),
+             "payload": good[:40] + bytes([good[40] ^ 0xFF]) + good[41:], "empty": b""}
+    for name, blob in cases.items():
+        want = port.frame_decompress(blob, len(b))[0]
+        assert want < 0, name
+        with pytest.raises(b200.LZ4FrameError) as e:
+            b200.decompress_frames(blob, len(b))
+        assert e.value.code == want, (name, e.value.code, want)
+    with pytest.raises(b200.LZ4FrameError) as e:
+        b200.decompress_frames(good, len(b) - 1)
+    assert e.value.code == -9

@@ -74,5 +74,35 @@ def main():
     t, med = timeit(lambda: B.xxh64_batch_dev(src, soff, slen, o64b, 0))
     print(f"xxh64 64KiB: {N/t/1e9:.0f} GB/s best", flush=True)
 
-if __name__ == "__main__":
+if __name__ == "__main__" and not os.environ.get("HC"):
     main()
+
+
+def hc_probe():
+    """config 4 shape: 256 KiB blocks, HC level 9 — ratio vs the reference's LZ4_compress_HC(9) and GiB/s"""
+    import ctypes
+    nblk = int(os.environ.get("HC_NBLK", 2048)); bs = 262144
+    chk = O.best_available()
+    base_n = min(nblk, 256)
+    host = chk.datagen(base_n * bs, 0.5, 0.0, 4)
+    dev = torch.device("cuda:0")
+    src = torch.from_numpy(host).to(dev).repeat((nblk + base_n - 1) // base_n)[: nblk * bs].contiguous()
+    bound = L.max_compressed_length(bs); stride = (bound + 15) // 16 * 16
+    soff = torch.arange(nblk, device=dev, dtype=torch.int64) * bs
+    slen = torch.full((nblk,), bs, device=dev, dtype=torch.int32)
+    coff = torch.arange(nblk, device=dev, dtype=torch.int64) * stride
+    ccap = torch.full((nblk,), bound, device=dev, dtype=torch.int32)
+    comp = torch.zeros(nblk * stride, device=dev, dtype=torch.uint8)
+    clen = torch.zeros(nblk, device=dev, dtype=torch.int32)
+    t, med = timeit(lambda: L.batch.compress_hc_batch_dev(src, soff, slen, comp, coff, ccap, clen, 9), iters=2, warm=1)
+    N = nblk * bs; C = int(clen.sum().item())
+    ref_c = sum(len(chk.compress_hc(host[i * bs:(i + 1) * bs], 9)) for i in range(4)) if hasattr(chk, "compress_hc") else 0
+    gpu_c4 = int(clen[:4].sum().item())
+    print(f"HC-9 256KiB x{nblk}: {N/t/2**30:.2f} GiB/s  ratio {N/C:.3f}  (first 4 blocks: ours {4*bs/gpu_c4:.3f} vs reference HC-9 {4*bs/max(ref_c,1):.3f})", flush=True)
+    out = torch.zeros(nblk * bs, device=dev, dtype=torch.uint8); res = torch.zeros(nblk, device=dev, dtype=torch.int32)
+    L.batch.decompress_safe_batch_dev(comp, coff, clen, out, soff, slen, res)
+    print("HC roundtrip ok:", bool((res == bs).all().item()) and bool(torch.equal(out, src)), flush=True)
+
+
+if __name__ == "__main__" and os.environ.get("HC"):
+    hc_probe()
