@@ -181,21 +181,26 @@ done:
 }
 
 // ---------------------------------------------------------------------------------------------
-// Decoupled parser ("v2"): candidate lookup + verification run AHEAD of the serial greedy parse.
+// Decoupled parser (algo 2, the default): candidate lookup + verification run AHEAD of the greedy parse.
 //
-// The v1 kernel above discovers one match, extends it, writes it, and only then knows where to probe
-// next: three dependent L2 round trips per ~27 input bytes with 13 warps/SM to hide them.  Here the
-// block is processed in windows of W positions and each window in two phases:
-//   AB (throughput, lane-parallel, no decisions): every position is hashed, looked up and INSERTED in
-//      order (32 per step, lookups of a step before its inserts), every candidate is verified and each
-//      lane measures its own match (forward up to CAP bytes, backward up to 4) — results go to a small
-//      per-warp array in shared memory plus a hit bitmap held in registers.  Four steps are in flight
-//      at once so their loads overlap; nothing here depends on the parse.
-//   C  (serial, cheap): the greedy walk only reads that array: next hit at or after ip from the bitmap
-//      (ballot/ffs/shuffle), distance + lengths by one shared-memory read, cooperative extension only
-//      for matches that hit CAP, then the usual sequence emission.
-// Inserting every position (not only those before a match start) costs no ratio: on the reference's
-// own generator the parse is slightly denser than lz4's (1.629 vs 1.612 at P=0.50).
+// The coupled kernel above discovers one match, extends it, writes it, and only then knows where to
+// probe next: three dependent L2 round trips and ~200 warp instructions per ~27 input bytes, with 13
+// warps/SM to hide them.  Here the block is walked in chunks of 128 positions, each in two phases:
+//
+//   AB (lane-parallel, no decisions): lane l owns the 4 consecutive positions of one aligned 32-bit
+//      word of the input (two coalesced word loads + three funnel shifts give its four 4-byte
+//      sequences).  All 128 positions are hashed, looked up and then INSERTED (every position, in
+//      order), all candidates are verified with four independent loads per lane, and the outcome is
+//      one 16-bit distance per position in shared memory (256 B per warp) plus a 128-bit hit mask in
+//      registers.  Nothing here depends on the parse.
+//   C  (serial, cheap): the greedy walk reads only that: next hit at or after ip from the mask
+//      (a few uniform ALU ops), its distance by one shared-memory read, ONE cooperative compare round
+//      for catch-up (lz4.c:1080) + the first 24 match bytes (lz4.c:1153), literal copy, and a record
+//      of the sequence in lane k's registers.  Tokens and offsets of 32 recorded sequences are then
+//      written by 32 lanes at once.
+//
+// Inserting every position (instead of only positions outside matches) costs no ratio: on the
+// reference's own generator the parse is slightly denser than lz4's (1.63 vs 1.61 at P=0.50).
 template <int HASH_LOG, bool U16>
 __global__ void __launch_bounds__(32)
 lz4_compress_fast2_kernel(const uint8_t* __restrict__ src_base, const uint64_t* __restrict__ src_off,
@@ -204,12 +209,10 @@ lz4_compress_fast2_kernel(const uint8_t* __restrict__ src_base, const uint64_t* 
                           const int32_t* __restrict__ dst_cap, int32_t* __restrict__ result, uint32_t nblocks)
 {
     using Entry = typename std::conditional<U16, uint16_t, uint32_t>::type;
-    constexpr int W = 256, STEPS = W / 32, G = 4, CAP = 32;    // 1 KiB of window state: 12 warps/SM next to a 16 KiB table
     constexpr int TABLE_BYTES = int(sizeof(Entry) << HASH_LOG);
     extern __shared__ __align__(128) uint8_t smem_raw[];
     Entry* table = reinterpret_cast<Entry*>(smem_raw);
-    uint16_t* s_dist = reinterpret_cast<uint16_t*>(smem_raw + TABLE_BYTES);        // [W] match distance, 0 = no match here
-    uint16_t* s_mlb = s_dist + W;                                                  // [W] forward length | backward length << 8
+    uint16_t* s_dist = reinterpret_cast<uint16_t*>(smem_raw + TABLE_BYTES);        // [128] match distance, 0 = no match at this position
 
     const uint32_t b = blockIdx.x;
     if (b >= nblocks) return;
@@ -226,105 +229,125 @@ lz4_compress_fast2_kernel(const uint8_t* __restrict__ src_base, const uint64_t* 
     {
         for (int i = lane; i < TABLE_BYTES / 16; i += 32) reinterpret_cast<uint4*>(table)[i] = make_uint4(0, 0, 0, 0);
         __syncwarp();
-        const InGlobal in{src};
-        const int mflimit = n - 12, matchlimit = n - 5;
+        // aligned-word view of the block: byte a of the view is position a - ph
+        const uint32_t ph = uint32_t(reinterpret_cast<uintptr_t>(src)) & 3u;
+        const uint32_t* __restrict__ wsrc = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(src) - ph);
+        auto ld4 = [&](int pos) -> uint32_t {                      // the 4 bytes at position pos (pos + 3 < n)
+            const uint32_t a = uint32_t(pos) + ph;
+            const uint32_t* w = wsrc + (a >> 2);
+            return __funnelshift_r(w[0], w[1], (a & 3u) * 8u);
+        };
+        const int mflimit = n - 12, matchlimit = n - 5;            // lz4.c:243-244
         int op = 0, anchor = 0, ip = 0;
-        bool have = false; Seq q = {0, 0, 0, 0};
+        // up to 32 found sequences wait in registers (lane k holds sequence k) for their token/offset bytes
+        int nrec = 0, r_o = 0, r_lit = 0, r_ml = 0, r_dist = 0;
 
-        for (int wbase = 0; wbase <= mflimit; wbase += W) {
-            if (lane < W / 128) {                                  // the window after next on its way to L2
-                const int pfq = wbase + 4 * W + lane * 128;
+        auto flush = [&]() {                                       // 32 lanes write 32 tokens / length chains / offsets
+            if (lane < nrec) {
+                const int mcode = r_ml - 4;
+                uint8_t* d = dst + r_o;
+                d[0] = uint8_t((min(r_lit, 15) << 4) | min(mcode, 15));
+                d += 1;
+                if (r_lit >= 15) { int v = r_lit - 15; for (; v >= 255; v -= 255) *d++ = 255; *d++ = uint8_t(v); }
+                d += r_lit;
+                d[0] = uint8_t(r_dist); d[1] = uint8_t(r_dist >> 8);                  // LE16 offset (lz4.c:1133)
+                d += 2;
+                if (mcode >= 15) { int v = mcode - 15; for (; v >= 255; v -= 255) *d++ = 255; *d++ = uint8_t(v); }
+            }
+            nrec = 0;
+        };
+
+        const int nchunks = (mflimit + int(ph)) / 128 + 1;
+        for (int c = 0; c < nchunks; c++) {
+            const int cp0 = 128 * c - int(ph);                     // position of the chunk's first byte
+            if (lane < 2) {                                        // two chunks ahead -> L2
+                const int pfq = cp0 + 512 + lane * 128;
                 if (pfq < n) asm volatile("prefetch.global.L2 [%0];" :: "l"(__cvta_generic_to_global(src + pfq)));
             }
             // ---------------- phase AB
-            uint32_t hitword = 0;                                  // lane s keeps the hit mask of step s
-            #pragma unroll 1
-            for (int g = 0; g < STEPS; g += G) {
-                uint32_t seq[G]; int cand[G]; bool plaus[G]; uint32_t cseq[G];
-                #pragma unroll
-                for (int k = 0; k < G; k++) {
-                    const int p = wbase + (g + k) * 32 + lane;
-                    seq[k] = in.ld4(min(p, mflimit));
-                }
-                #pragma unroll
-                for (int k = 0; k < G; k++) {                      // table traffic in position order
-                    const int p = wbase + (g + k) * 32 + lane;
-                    const uint32_t h = (seq[k] * 2654435761u) >> (32 - HASH_LOG);
-                    cand[k] = table[h];
-                    if (p <= mflimit) table[h] = Entry(p);
-                    plaus[k] = p <= mflimit && cand[k] < p && (U16 || p - cand[k] <= 65535);
-                }
-                #pragma unroll
-                for (int k = 0; k < G; k++) {
-                    const int p = wbase + (g + k) * 32 + lane;
-                    cseq[k] = in.ld4(plaus[k] ? cand[k] : min(p, mflimit));
-                }
-                #pragma unroll
-                for (int k = 0; k < G; k++) {
-                    const int p = wbase + (g + k) * 32 + lane;
-                    const bool hit = plaus[k] && cseq[k] == seq[k];
-                    int ml = 0, back = 0;
-                    if (hit) {
-                        const int c = cand[k];
-                        const int maxlen = min(matchlimit - p, CAP);
-                        ml = 4;
-                        while (ml < maxlen) {
-                            const uint32_t x = in.ld4(p + ml) ^ in.ld4(c + ml);
-                            if (x) { ml += (__ffs(x) - 1) >> 3; break; }
-                            ml += 4;
-                        }
-                        ml = min(ml, maxlen);
-                        if (c >= 4) {                               // catch-up potential: equal bytes just before both
-                            const uint32_t x = in.ld4(p - 4) ^ in.ld4(c - 4);
-                            back = x ? (__clz(x) >> 3) : 4;
-                        }
-                    }
-                    const int idx = (g + k) * 32 + lane;
-                    s_dist[idx] = hit ? uint16_t(p - cand[k]) : uint16_t(0);
-                    s_mlb[idx] = uint16_t(ml | (back << 8));
-                    const uint32_t m = __ballot_sync(B200_FULL, hit);
-                    if (lane == g + k) hitword = m;
-                }
+            const int p0 = cp0 + 4 * lane;
+            uint32_t w0 = 0, w1 = 0;
+            if (p0 + 3 >= 0 && p0 <= mflimit) { w0 = wsrc[32 * c + lane]; w1 = wsrc[32 * c + lane + 1]; }
+            uint32_t seq[4], h[4]; int cand[4]; bool plaus[4];
+            seq[0] = w0; seq[1] = __funnelshift_r(w0, w1, 8); seq[2] = __funnelshift_r(w0, w1, 16); seq[3] = __funnelshift_r(w0, w1, 24);
+            #pragma unroll
+            for (int j = 0; j < 4; j++) { h[j] = (seq[j] * 2654435761u) >> (32 - HASH_LOG); cand[j] = table[h[j]]; }
+            #pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int p = p0 + j;
+                const bool valid = p >= 0 && p <= mflimit;
+                if (valid) table[h[j]] = Entry(p);
+                plaus[j] = valid && cand[j] < p && (U16 || p - cand[j] <= 65535);
             }
+            uint32_t cseq[4];
+            #pragma unroll
+            for (int j = 0; j < 4; j++) cseq[j] = plaus[j] ? ld4(cand[j]) : ~seq[j];
+            uint32_t nib = 0; uint32_t d01, d23;
+            {
+                uint32_t dd[4];
+                #pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const bool hit = cseq[j] == seq[j];            // implies plaus (otherwise cseq = ~seq)
+                    dd[j] = hit ? uint32_t(p0 + j - cand[j]) : 0u;
+                    nib |= uint32_t(hit) << j;
+                }
+                d01 = dd[0] | (dd[1] << 16); d23 = dd[2] | (dd[3] << 16);
+            }
+            reinterpret_cast<uint2*>(s_dist)[lane] = make_uint2(d01, d23);
+            // position-ordered hit mask: word k = positions cp0+32k .. +31 (8 lanes x 4 bits)
+            const uint32_t gw = __reduce_or_sync(0xFFu << (lane & 24), nib << (4 * (lane & 7)));
+            const uint32_t hw0 = __shfl_sync(B200_FULL, gw, 0), hw1 = __shfl_sync(B200_FULL, gw, 8),
+                           hw2 = __shfl_sync(B200_FULL, gw, 16), hw3 = __shfl_sync(B200_FULL, gw, 24);
             __syncwarp();
-            // ---------------- phase C: greedy walk over this window's hits
-            const int wend = min(wbase + W, mflimit + 1);
-            if (ip < wbase) ip = wbase;
-            while (ip < wend) {
-                const int r = ip - wbase;
-                uint32_t mine = 0;
-                if (lane < STEPS) {
-                    if (lane == (r >> 5)) mine = hitword & (0xFFFFFFFFu << (r & 31));
-                    else if (lane > (r >> 5)) mine = hitword;
+            // ---------------- phase C: greedy walk over this chunk's hits
+            for (;;) {
+                int r = ip - cp0;
+                if (r < 0) r = 0;
+                if (r >= 128) break;
+                int q;
+                {   // first hit at or after r
+                    const int k0 = r >> 5;
+                    const uint32_t first_mask = 0xFFFFFFFFu << (r & 31);
+                    uint32_t m0 = k0 == 0 ? (hw0 & first_mask) : 0u;
+                    uint32_t m1 = k0 == 1 ? (hw1 & first_mask) : (k0 < 1 ? hw1 : 0u);
+                    uint32_t m2 = k0 == 2 ? (hw2 & first_mask) : (k0 < 2 ? hw2 : 0u);
+                    uint32_t m3 = k0 == 3 ? (hw3 & first_mask) : hw3;
+                    if (m0) q = __ffs(m0) - 1;
+                    else if (m1) q = 32 + __ffs(m1) - 1;
+                    else if (m2) q = 64 + __ffs(m2) - 1;
+                    else if (m3) q = 96 + __ffs(m3) - 1;
+                    else break;
                 }
-                const uint32_t any = __ballot_sync(B200_FULL, mine != 0);
-                if (any == 0) break;
-                const int wi = __ffs(any) - 1;
-                const uint32_t wv = __shfl_sync(B200_FULL, mine, wi);
-                const int qi = wi * 32 + __ffs(wv) - 1;             // window-relative position of the next match
-                int ms = wbase + qi;
-                const int dist = s_dist[qi];
-                const uint32_t mlb = s_mlb[qi];
-                int ml = int(mlb & 0xFF);
-                const int back = min(int(mlb >> 8), ms - anchor);
-                if (ml == CAP && ms + ml < matchlimit)
-                    ml += match_extend(in, ms + ml, ms - dist + ml, matchlimit - (ms + ml), lane);
-                // write the PREVIOUS sequence now (its literal bytes were requested one iteration ago)
-                uint32_t litv = 0;
-                if (have) {
-                    if (lane < q.ms - q.anchor && q.ms - q.anchor <= 32) litv = in.ld1(q.anchor + lane);
-                    if (!emit_sequence(in, q, litv, dst, op, cap, lane)) goto done;
+                int ms = cp0 + q;
+                const int dist = s_dist[q];
+                int mc = ms - dist, ml;
+                {   // one cooperative round: lane j compares offset d = j-8 (catch-up) .. +23 (match body)
+                    const int d = lane - 8;
+                    const int backroom = min(ms - anchor, mc);
+                    const bool ok = d < 0 ? (-d <= backroom) : (ms + d < matchlimit);
+                    const bool eq = ok && src[ms + d] == src[mc + d];
+                    const unsigned e = __ballot_sync(B200_FULL, eq);
+                    const int back = __clz((~e) & 0xFFu) - 24;
+                    const int fwd = __ffs((~(e >> 8)) | (1u << 24)) - 1;
+                    ml = fwd;
+                    if (fwd == 24) ml += match_extend(InGlobal{src}, ms + 24, mc + 24, matchlimit - (ms + 24), lane);
+                    ms -= back; ml += back;
                 }
-                ms -= back; ml += back;
-                q.anchor = anchor; q.ms = ms; q.off = dist; q.ml = ml; have = true;
+                // sizes, literal copy now (offsets are known sequentially), header bytes later in batch
+                const int lit = ms - anchor, mcode = ml - 4;
+                const int lhdr = lit >= 15 ? (lit - 15) / 255 + 1 : 0;
+                const int mhdr = mcode >= 15 ? (mcode - 15) / 255 + 1 : 0;
+                const int size = 1 + lhdr + lit + 2 + mhdr;
+                if ((long long)op + size > cap) goto done;                            // lz4.c:1085-1088, 1158
+                warp_copy(dst + op + 1 + lhdr, src + anchor, lit, lane);
+                if (lane == nrec) { r_o = op; r_lit = lit; r_ml = ml; r_dist = dist; }
+                nrec++;
+                if (nrec == 32) flush();
+                op += size;
                 ip = anchor = ms + ml;
             }
         }
-        if (have) {
-            uint32_t litv = 0;
-            if (lane < q.ms - q.anchor && q.ms - q.anchor <= 32) litv = in.ld1(q.anchor + lane);
-            if (!emit_sequence(in, q, litv, dst, op, cap, lane)) goto done;
-        }
+        flush();
         {   // last literals (lz4.c:1266-1293)
             const int lit = n - anchor;
             const int lhdr = lit >= 15 ? (lit - 15) / 255 + 1 : 0;
@@ -344,7 +367,7 @@ done:
 template <int HASH_LOG, bool U16>
 static cudaError_t launch_v2(const BatchArgs& a, cudaStream_t st)
 {
-    const size_t smem = ((U16 ? 2u : 4u) << HASH_LOG) + 2 * 256 * sizeof(uint16_t);
+    const size_t smem = ((U16 ? 2u : 4u) << HASH_LOG) + 128 * sizeof(uint16_t);
     auto k = lz4_compress_fast2_kernel<HASH_LOG, U16>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
