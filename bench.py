@@ -183,6 +183,7 @@ def run_b200(args):
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     if world > 1 and not dist.is_initialized():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG", "WARN")          # keep NCCL's version banner off stdout (one JSON line)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -336,7 +337,7 @@ def run_b200(args):
             "compress_gibs": total_bytes / (t_comp_ms / 1e3) / GIB,
             "decompress_gibs": total_bytes / (t_dec_ms / 1e3) / GIB,
             "ratio": total_bytes / total_comp,
-            "roofline": {"bound": "hbm", "kernel": "lz4_compress_fast_kernel", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "lz4_compress_fast2_kernel<13,u16>" if args.hash_log == 13 else "lz4_compress_fast2_kernel<12,u16>", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "frac_of_nominal_8TBs": achieved / 8000.0,
                          "traffic": traffic, "algorithmic_bytes_per_launch": algo_bytes, "peak_source": peak_src,
                          "decompress_achieved": algo_bytes / (t_dec_ms / 1e3) / 1e9},

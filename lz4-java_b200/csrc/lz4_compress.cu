@@ -298,6 +298,8 @@ lz4_compress_fast2_kernel(const uint8_t* __restrict__ src_base, const uint64_t* 
             const uint32_t gw = __reduce_or_sync(0xFFu << (lane & 24), nib << (4 * (lane & 7)));
             const uint32_t hw0 = __shfl_sync(B200_FULL, gw, 0), hw1 = __shfl_sync(B200_FULL, gw, 8),
                            hw2 = __shfl_sync(B200_FULL, gw, 16), hw3 = __shfl_sync(B200_FULL, gw, 24);
+            const unsigned long long hlo = (unsigned long long)hw0 | ((unsigned long long)hw1 << 32);
+            const unsigned long long hhi = (unsigned long long)hw2 | ((unsigned long long)hw3 << 32);
             __syncwarp();
             // ---------------- phase C: greedy walk over this chunk's hits
             for (;;) {
@@ -305,18 +307,15 @@ lz4_compress_fast2_kernel(const uint8_t* __restrict__ src_base, const uint64_t* 
                 if (r < 0) r = 0;
                 if (r >= 128) break;
                 int q;
-                {   // first hit at or after r
-                    const int k0 = r >> 5;
-                    const uint32_t first_mask = 0xFFFFFFFFu << (r & 31);
-                    uint32_t m0 = k0 == 0 ? (hw0 & first_mask) : 0u;
-                    uint32_t m1 = k0 == 1 ? (hw1 & first_mask) : (k0 < 1 ? hw1 : 0u);
-                    uint32_t m2 = k0 == 2 ? (hw2 & first_mask) : (k0 < 2 ? hw2 : 0u);
-                    uint32_t m3 = k0 == 3 ? (hw3 & first_mask) : hw3;
-                    if (m0) q = __ffs(m0) - 1;
-                    else if (m1) q = 32 + __ffs(m1) - 1;
-                    else if (m2) q = 64 + __ffs(m2) - 1;
-                    else if (m3) q = 96 + __ffs(m3) - 1;
-                    else break;
+                {   // first hit at or after r: two 64-bit halves of the 128-bit position-ordered mask
+                    const unsigned long long lo = r < 64 ? (hlo >> r) : 0ull;
+                    if (lo) q = r + __ffsll((long long)lo) - 1;
+                    else {
+                        const int r2 = max(r - 64, 0);
+                        const unsigned long long hi = hhi >> r2;
+                        if (hi == 0) break;
+                        q = 64 + r2 + __ffsll((long long)hi) - 1;
+                    }
                 }
                 int ms = cp0 + q;
                 const int dist = s_dist[q];
@@ -338,7 +337,7 @@ lz4_compress_fast2_kernel(const uint8_t* __restrict__ src_base, const uint64_t* 
                 const int lhdr = lit >= 15 ? (lit - 15) / 255 + 1 : 0;
                 const int mhdr = mcode >= 15 ? (mcode - 15) / 255 + 1 : 0;
                 const int size = 1 + lhdr + lit + 2 + mhdr;
-                if ((long long)op + size > cap) goto done;                            // lz4.c:1085-1088, 1158
+                if (uint32_t(op) + uint32_t(size) > uint32_t(cap)) goto done;         // lz4.c:1085-1088, 1158 (op <= cap < 2^31)
                 warp_copy(dst + op + 1 + lhdr, src + anchor, lit, lane);
                 if (lane == nrec) { r_o = op; r_lit = lit; r_ml = ml; r_dist = dist; }
                 nrec++;

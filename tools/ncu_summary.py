@@ -26,7 +26,7 @@ def main(rep, top=0.008):
                 print(f"  {k:66s} {d[k][1]:>22s} {d[k][0]}")
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
-    hdr = rows[1]; data = [r for r in rows[2:] if len(r) == len(hdr)]
+    hdr = rows[1]; data = [r for r in rows[2:] if len(r) == len(hdr) and r[hdr.index("Instructions Executed")].isdigit()]
     ix = {h: i for i, h in enumerate(hdr)}
     tot = sum(int(r[ix["Instructions Executed"]]) for r in data)
     smp = sum(int(r[ix["# Samples"]]) for r in data) or 1
