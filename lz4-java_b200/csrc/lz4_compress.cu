@@ -295,7 +295,8 @@ lz4_compress_fast2_kernel(const uint8_t* __restrict__ src_base, const uint64_t* 
             }
             reinterpret_cast<uint2*>(s_dist)[lane] = make_uint2(d01, d23);
             // position-ordered hit mask: word k = positions cp0+32k .. +31 (8 lanes x 4 bits)
-            const uint32_t gw = __reduce_or_sync(0xFFu << (lane & 24), nib << (4 * (lane & 7)));
+            uint32_t gw = nib << (4 * (lane & 7));            // OR over each group of 8 lanes (butterfly: all lanes in step)
+            gw |= __shfl_xor_sync(B200_FULL, gw, 1); gw |= __shfl_xor_sync(B200_FULL, gw, 2); gw |= __shfl_xor_sync(B200_FULL, gw, 4);
             const uint32_t hw0 = __shfl_sync(B200_FULL, gw, 0), hw1 = __shfl_sync(B200_FULL, gw, 8),
                            hw2 = __shfl_sync(B200_FULL, gw, 16), hw3 = __shfl_sync(B200_FULL, gw, 24);
             const unsigned long long hlo = (unsigned long long)hw0 | ((unsigned long long)hw1 << 32);
@@ -376,6 +377,223 @@ static cudaError_t launch_v2(const BatchArgs& a, cudaStream_t st)
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------
+// Two-warp pipeline (algo 3): the decoupled parser above, split across a producer/consumer pair so the
+// serial walk carries nothing but the walk.
+//
+//   warp L ("lookup + layout"): phase AB for chunk s, then writes out the sequences the parser found
+//                               in chunk s-2 (sizes, prefix sum of output offsets, 32 tokens/offsets by
+//                               32 lanes, cooperative literal copies) — all throughput work.
+//   warp P ("parser"):          greedy walk of chunk s-1: next hit, its distance, one cooperative
+//                               compare round, and a 16-byte record in shared memory.  ~65 instructions
+//                               and one L2 round trip per sequence instead of ~130 + the copies.
+// One CTA barrier per 128-position chunk hands the double-buffered chunk state (distances, hit mask,
+// records) over.  Same parse, same output bytes as algo 2.
+struct SeqRec { int anchor, ms, dist, ml; };
+
+template <int HASH_LOG, bool U16>
+__global__ void __launch_bounds__(64)
+lz4_compress_fast3_kernel(const uint8_t* __restrict__ src_base, const uint64_t* __restrict__ src_off,
+                          const int32_t* __restrict__ src_len,
+                          uint8_t* __restrict__ dst_base, const uint64_t* __restrict__ dst_off,
+                          const int32_t* __restrict__ dst_cap, int32_t* __restrict__ result, uint32_t nblocks)
+{
+    using Entry = typename std::conditional<U16, uint16_t, uint32_t>::type;
+    constexpr int TABLE_BYTES = int(sizeof(Entry) << HASH_LOG);
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    Entry* table = reinterpret_cast<Entry*>(smem_raw);
+    uint16_t* s_dist = reinterpret_cast<uint16_t*>(smem_raw + TABLE_BYTES);                 // [2][128]
+    SeqRec* s_rec = reinterpret_cast<SeqRec*>(smem_raw + TABLE_BYTES + 512);                // [2][32]
+    uint32_t* s_mask = reinterpret_cast<uint32_t*>(smem_raw + TABLE_BYTES + 512 + 1024);    // [2][4]
+    int* s_cnt = reinterpret_cast<int*>(s_mask + 8);                                        // [2] records per buffer, [2] = final anchor
+
+    const uint32_t b = blockIdx.x;
+    if (b >= nblocks) return;
+    const int lane = lane_id();
+    const bool isL = (threadIdx.x >> 5) == 0;
+    const uint8_t* __restrict__ src = src_base + src_off[b];
+    uint8_t* __restrict__ dst = dst_base + dst_off[b];
+    const int n = src_len[b];
+    const int cap = dst_cap[b];
+
+    if (n < 0 || n > 0x7E000000 || (U16 && n >= 65536 + 11)) { if (threadIdx.x == 0) result[b] = 0; return; }   // lz4.c:1324, 973
+    if (n == 0) { if (threadIdx.x == 0) { if (cap >= 1) dst[0] = 0; result[b] = cap >= 1 ? 1 : 0; } return; }
+
+    const uint32_t ph = uint32_t(reinterpret_cast<uintptr_t>(src)) & 3u;
+    const uint32_t* __restrict__ wsrc = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(src) - ph);
+    const int mflimit = n - 12, matchlimit = n - 5;
+    const int nchunks = (mflimit + int(ph)) / 128 + 1;
+
+    if (isL) {
+        for (int i = lane; i < TABLE_BYTES / 16; i += 32) reinterpret_cast<uint4*>(table)[i] = make_uint4(0, 0, 0, 0);
+        if (lane < 3) s_cnt[lane] = 0;
+        __syncwarp();
+    }
+    auto ld4 = [&](int pos) -> uint32_t {
+        const uint32_t a = uint32_t(pos) + ph;
+        const uint32_t* w = wsrc + (a >> 2);
+        return __funnelshift_r(w[0], w[1], (a & 3u) * 8u);
+    };
+
+    int op = 0; bool fail = false;          // warp L
+    int ip = 0, anchor = 0;                 // warp P
+    asm volatile("bar.sync 1, 64;" ::: "memory");
+
+    for (int s = 0; s < nchunks + 2; s++) {
+        if (isL) {
+            // ---------------- phase AB for chunk s
+            if (s < nchunks) {
+                const int c = s, cp0 = 128 * c - int(ph), buf = c & 1;
+                if (lane < 2) {
+                    const int pfq = cp0 + 512 + lane * 128;
+                    if (pfq < n) asm volatile("prefetch.global.L2 [%0];" :: "l"(__cvta_generic_to_global(src + pfq)));
+                }
+                const int p0 = cp0 + 4 * lane;
+                uint32_t w0 = 0, w1 = 0;
+                if (p0 + 3 >= 0 && p0 <= mflimit) { w0 = wsrc[32 * c + lane]; w1 = wsrc[32 * c + lane + 1]; }
+                uint32_t seq[4], h[4]; int cand[4]; bool plaus[4];
+                seq[0] = w0; seq[1] = __funnelshift_r(w0, w1, 8); seq[2] = __funnelshift_r(w0, w1, 16); seq[3] = __funnelshift_r(w0, w1, 24);
+                #pragma unroll
+                for (int j = 0; j < 4; j++) { h[j] = (seq[j] * 2654435761u) >> (32 - HASH_LOG); cand[j] = table[h[j]]; }
+                #pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int p = p0 + j;
+                    const bool valid = p >= 0 && p <= mflimit;
+                    if (valid) table[h[j]] = Entry(p);
+                    plaus[j] = valid && cand[j] < p && (U16 || p - cand[j] <= 65535);
+                }
+                uint32_t cseq[4];
+                #pragma unroll
+                for (int j = 0; j < 4; j++) cseq[j] = plaus[j] ? ld4(cand[j]) : ~seq[j];
+                uint32_t nib = 0, dd[4];
+                #pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const bool hit = cseq[j] == seq[j];
+                    dd[j] = hit ? uint32_t(p0 + j - cand[j]) : 0u;
+                    nib |= uint32_t(hit) << j;
+                }
+                reinterpret_cast<uint2*>(s_dist + 128 * buf)[lane] = make_uint2(dd[0] | (dd[1] << 16), dd[2] | (dd[3] << 16));
+                uint32_t gw = nib << (4 * (lane & 7));        // OR over each group of 8 lanes (butterfly: all lanes in step)
+                gw |= __shfl_xor_sync(B200_FULL, gw, 1); gw |= __shfl_xor_sync(B200_FULL, gw, 2); gw |= __shfl_xor_sync(B200_FULL, gw, 4);
+                if ((lane & 7) == 0) s_mask[4 * buf + (lane >> 3)] = gw;
+            }
+            // ---------------- write out the sequences of chunk s-2
+            if (s >= 2 && !fail) {
+                const int buf = s & 1;
+                const int cnt = s_cnt[buf];
+                SeqRec r = {0, 0, 0, 4};
+                if (lane < cnt) r = s_rec[32 * buf + lane];
+                const int lit = r.ms - r.anchor, mcode = r.ml - 4;
+                const int lhdr = lit >= 15 ? (lit - 15) / 255 + 1 : 0;
+                const int mhdr = mcode >= 15 ? (mcode - 15) / 255 + 1 : 0;
+                const int size = lane < cnt ? 1 + lhdr + lit + 2 + mhdr : 0;
+                int incl = size;
+                #pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(B200_FULL, incl, d); if (lane >= d) incl += y; }
+                const int total = __shfl_sync(B200_FULL, incl, 31);
+                if (uint32_t(op) + uint32_t(total) > uint32_t(cap)) fail = true;                  // lz4.c:1085-1088, 1158
+                else {
+                    const int o = op + incl - size;
+                    if (lane < cnt) {
+                        uint8_t* d = dst + o;
+                        d[0] = uint8_t((min(lit, 15) << 4) | min(mcode, 15));
+                        d += 1;
+                        if (lit >= 15) { int v = lit - 15; for (; v >= 255; v -= 255) *d++ = 255; *d++ = uint8_t(v); }
+                        d += lit;
+                        d[0] = uint8_t(r.dist); d[1] = uint8_t(r.dist >> 8);                     // LE16 offset (lz4.c:1133)
+                        d += 2;
+                        if (mcode >= 15) { int v = mcode - 15; for (; v >= 255; v -= 255) *d++ = 255; *d++ = uint8_t(v); }
+                    }
+                    for (int k = 0; k < cnt; k++) {                                               // literal runs, one cooperative copy each
+                        const int ka = __shfl_sync(B200_FULL, r.anchor, k);
+                        const int kl = __shfl_sync(B200_FULL, lit, k);
+                        const int ko = __shfl_sync(B200_FULL, o + 1 + lhdr, k);
+                        warp_copy(dst + ko, src + ka, kl, lane);
+                    }
+                    op += total;
+                }
+            }
+        } else {
+            // ---------------- warp P: greedy walk of chunk s-1
+            if (s >= 1 && s <= nchunks) {
+                const int c = s - 1, cp0 = 128 * c - int(ph), buf = c & 1;
+                const unsigned long long hlo = (unsigned long long)s_mask[4 * buf] | ((unsigned long long)s_mask[4 * buf + 1] << 32);
+                const unsigned long long hhi = (unsigned long long)s_mask[4 * buf + 2] | ((unsigned long long)s_mask[4 * buf + 3] << 32);
+                int k = 0;
+                for (;;) {
+                    int r = ip - cp0;
+                    if (r < 0) r = 0;
+                    if (r >= 128) break;
+                    int q;
+                    {
+                        const unsigned long long lo = r < 64 ? (hlo >> r) : 0ull;
+                        if (lo) q = r + __ffsll((long long)lo) - 1;
+                        else {
+                            const int r2 = max(r - 64, 0);
+                            const unsigned long long hi = hhi >> r2;
+                            if (hi == 0) break;
+                            q = 64 + r2 + __ffsll((long long)hi) - 1;
+                        }
+                    }
+                    int ms = cp0 + q;
+                    const int dist = s_dist[128 * buf + q];
+                    const int mc = ms - dist;
+                    int ml;
+                    {
+                        const int d = lane - 8;
+                        const int backroom = min(ms - anchor, mc);
+                        const bool ok = d < 0 ? (-d <= backroom) : (ms + d < matchlimit);
+                        const bool eq = ok && src[ms + d] == src[mc + d];
+                        const unsigned e = __ballot_sync(B200_FULL, eq);
+                        const int back = __clz((~e) & 0xFFu) - 24;
+                        const int fwd = __ffs((~(e >> 8)) | (1u << 24)) - 1;
+                        ml = fwd;
+                        if (fwd == 24) ml += match_extend(InGlobal{src}, ms + 24, mc + 24, matchlimit - (ms + 24), lane);
+                        ms -= back; ml += back;
+                    }
+                    if (lane == 0) s_rec[32 * buf + k] = SeqRec{anchor, ms, dist, ml};
+                    k++;
+                    ip = anchor = ms + ml;
+                }
+                if (lane == 0) { s_cnt[buf] = k; s_cnt[2] = anchor; }
+            } else if (s > nchunks && lane == 0) {
+                s_cnt[(s - 1) & 1] = 0;          // nothing was parsed for this parity in the drain step
+            }
+        }
+        asm volatile("bar.sync 1, 64;" ::: "memory");
+    }
+
+    if (isL) {
+        int ret = 0;
+        if (!fail) {   // last literals (lz4.c:1266-1293)
+            const int fin = s_cnt[2];
+            const int lit = n - fin;
+            const int lhdr = lit >= 15 ? (lit - 15) / 255 + 1 : 0;
+            if (uint32_t(op) + 1u + uint32_t(lhdr) + uint32_t(lit) <= uint32_t(cap)) {
+                if (lane == 0) dst[op] = uint8_t(min(lit, 15) << 4);
+                op += 1;
+                if (lhdr) { write_len_ext(dst + op, lit - 15, lhdr, lane); op += lhdr; }
+                warp_copy(dst + op, src + fin, lit, lane);
+                ret = op + lit;
+            }
+        }
+        if (lane == 0) result[b] = ret;
+    }
+}
+
+template <int HASH_LOG, bool U16>
+static cudaError_t launch_v3(const BatchArgs& a, cudaStream_t st)
+{
+    const size_t smem = ((U16 ? 2u : 4u) << HASH_LOG) + 512 + 1024 + 32 + 16;
+    auto k = lz4_compress_fast3_kernel<HASH_LOG, U16>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    k<<<(unsigned)a.n, 64, smem, st>>>(a.src_base, a.src_off, a.src_len, a.dst_base, a.dst_off, a.dst_cap,
+                                       a.result, (uint32_t)a.n);
+    return cudaGetLastError();
+}
+
 template <int HASH_LOG, bool U16, bool STAGE>
 static cudaError_t launch_variant(const BatchArgs& a, cudaStream_t st)
 {
@@ -394,13 +612,18 @@ static cudaError_t launch_variant(const BatchArgs& a, cudaStream_t st)
 extern "C" {
 int b200lz4_compress_hash_log = 13;   // 13 = the reference's table size for <64 KiB blocks (lz4.c:756-762)
 int b200lz4_compress_stage = 0;       // 1 = stage <=64 KiB blocks in shared memory via TMA (v1 parser only)
-int b200lz4_compress_algo = 2;        // 2 = decoupled lookup/parse (default), 1 = the original coupled warp parser
+int b200lz4_compress_algo = 3;        // 3 = decoupled, two-warp pipeline (default); 2 = decoupled, one warp; 1 = coupled warp parser
 }
 
 cudaError_t launch_compress_fast(const BatchArgs& a, int max_src_len, cudaStream_t st)
 {
     if (a.n == 0) return cudaSuccess;
     const bool u16 = max_src_len > 0 && max_src_len <= 65536;
+    if (b200lz4_compress_algo == 3 && !b200lz4_compress_stage) {
+        if (!u16) return launch_v3<12, false>(a, st);
+        if (b200lz4_compress_hash_log == 12) return launch_v3<12, true>(a, st);
+        return launch_v3<13, true>(a, st);
+    }
     if (b200lz4_compress_algo == 2 && !b200lz4_compress_stage) {
         if (!u16) return launch_v2<12, false>(a, st);
         if (b200lz4_compress_hash_log == 12) return launch_v2<12, true>(a, st);

@@ -43,9 +43,9 @@ def main():
     N = nblk * bs
     import ctypes
     lib = L._native.lib()
-    variants = os.environ.get("VARIANTS", "13:0:2,12:0:2,13:0:1,12:0:1")
+    variants = os.environ.get("VARIANTS", "13:0:3,12:0:3,13:0:2,12:0:2,13:0:1")
     for v in variants.split(","):
-        hl, stage, algo = (int(x) for x in (v.split(":") + ["2"])[:3])
+        hl, stage, algo = (int(x) for x in (v.split(":") + ["3"])[:3])
         ctypes.c_int.in_dll(lib, "b200lz4_compress_hash_log").value = hl
         ctypes.c_int.in_dll(lib, "b200lz4_compress_stage").value = stage
         ctypes.c_int.in_dll(lib, "b200lz4_compress_algo").value = algo
