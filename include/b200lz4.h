@@ -156,6 +156,22 @@ int64_t b200lz4f_decode_dev(void* index, const uint8_t* d_src, uint8_t* d_slots,
                             int32_t* block_len_out, void* stream);
 void    b200lz4f_index_free(void* index);
 
+/* ---------------------------------------------------------------- lz4-java's containers as whole-buffer calls
+ * LZ4 Frame writer (LZ4FrameOutputStream.java:178-251): independent blocks of 64 KiB..4 MiB (bsCode 4..7), blocks that
+ * do not shrink are stored raw; flags bit0 = content checksum, bit1 = block checksums, bit2 = content size.
+ * "LZ4Block" container (LZ4BlockOutputStream.java:203-266 / LZ4BlockInputStream.java:191-264): 21-byte block
+ * headers, XXH32 (seed 0x9747b28c, 28-bit) of each original block, fast decompressor on the read side.
+ * Length-prefixed blocks (LZ4CompressorWithLength / LZ4DecompressorWithLength).
+ * Return: bytes written / decoded, or negative: -1 premature end, -2 corrupted, -9 dst too small, B200LZ4_E_*. */
+size_t  b200lz4f_compress_bound(size_t srcSize, int bsCode);
+int64_t b200lz4f_compress_host(const uint8_t* src, size_t srcSize, uint8_t* dst, size_t dstCapacity, int bsCode, int flags);
+size_t  b200lz4block_compress_bound(size_t srcSize, int blockSize);
+int64_t b200lz4block_compress_host(const uint8_t* src, size_t srcSize, uint8_t* dst, size_t dstCapacity, int blockSize);
+int64_t b200lz4block_decompress_host(const uint8_t* src, size_t srcSize, uint8_t* dst, size_t dstCapacity);
+int     b200lz4_compress_with_length(const char* src, char* dst, int srcSize, int dstCapacity);
+int     b200lz4_decompressed_length(const char* src);
+int     b200lz4_decompress_with_length(const char* src, int srcAvail, char* dst, int dstCapacity);
+
 /* kernel-launch counter (bench.py's "gpu_launches"): number of kernels this library has
  * launched from the calling process since load / since the last reset. */
 uint64_t b200lz4_launch_count(void);

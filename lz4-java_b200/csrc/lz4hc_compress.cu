@@ -22,24 +22,24 @@
 
 namespace b200 {
 
-static constexpr int HC_BUCKET_LOG = 11;               // 2048 buckets x 32 ways x 2 B = 128 KiB
+// bucket count is a template parameter: 2048 buckets (128 KiB, 1 CTA/SM) or 1024 buckets (64 KiB, 3 CTAs/SM)
 static constexpr int HC_WAYS = 32;
 static constexpr int HC_LANE_CAP = 64;                 // per-lane extension cap; the winner is extended cooperatively
-static constexpr size_t HC_SMEM = (size_t(2) << HC_BUCKET_LOG) * HC_WAYS + (size_t(4) << HC_BUCKET_LOG);
+template <int BL> constexpr size_t hc_smem() { return (size_t(2) << BL) * HC_WAYS + (size_t(4) << BL); }
 
 struct HcTable {
     uint16_t* ring;      // [bucket][way]
     uint32_t* head;      // [bucket] number of insertions so far
 };
 
-__device__ __forceinline__ uint32_t hc_hash(uint32_t seq) { return (seq * 2654435761u) >> (32 - HC_BUCKET_LOG); }
+template <int BL> __device__ __forceinline__ uint32_t hc_hash(uint32_t seq) { return (seq * 2654435761u) >> (32 - BL); }
 
 // insert positions [lo, hi) — every position, like LZ4HC_Insert
-template <class In>
+template <int BL, class In>
 __device__ __forceinline__ void hc_insert(const In& in, const HcTable& t, int lo, int hi, int lane)
 {
     for (int p = lo + lane; p < hi; p += 32) {
-        const uint32_t h = hc_hash(in.ld4(p));
+        const uint32_t h = hc_hash<BL>(in.ld4(p));
         const uint32_t slot = atomicAdd(&t.head[h], 1u) & (HC_WAYS - 1);
         t.ring[h * HC_WAYS + slot] = uint16_t(p);
     }
@@ -47,11 +47,11 @@ __device__ __forceinline__ void hc_insert(const In& in, const HcTable& t, int lo
 }
 
 // longest match for position p among the bucket's 32 most recent occurrences: returns ml (0 if < 4) and distance
-template <class In>
+template <int BL, class In>
 __device__ __forceinline__ int hc_search(const In& in, const HcTable& t, int p, int matchlimit, int lane, int& dist_out)
 {
     const uint32_t seq = in.ld4(p);
-    const uint32_t h = hc_hash(seq);
+    const uint32_t h = hc_hash<BL>(seq);
     const uint32_t cnt = t.head[h];
     const uint32_t c16 = t.ring[h * HC_WAYS + lane];
     const int dist = int((uint32_t(p) - c16) & 0xFFFFu);          // window-relative: any alias is re-verified on the bytes
@@ -77,6 +77,7 @@ __device__ __forceinline__ int hc_search(const In& in, const HcTable& t, int p, 
     return bml;
 }
 
+template <int BL>
 __global__ void __launch_bounds__(32)
 lz4hc_compress_kernel(const uint8_t* __restrict__ src_base, const uint64_t* __restrict__ src_off,
                       const int32_t* __restrict__ src_len,
@@ -86,7 +87,7 @@ lz4hc_compress_kernel(const uint8_t* __restrict__ src_base, const uint64_t* __re
     extern __shared__ __align__(16) uint8_t smem_raw[];
     HcTable t;
     t.ring = reinterpret_cast<uint16_t*>(smem_raw);
-    t.head = reinterpret_cast<uint32_t*>(smem_raw + (size_t(2) << HC_BUCKET_LOG) * HC_WAYS);
+    t.head = reinterpret_cast<uint32_t*>(smem_raw + (size_t(2) << BL) * HC_WAYS);
 
     const uint32_t b = blockIdx.x;
     if (b >= nblocks) return;
@@ -100,7 +101,7 @@ lz4hc_compress_kernel(const uint8_t* __restrict__ src_base, const uint64_t* __re
     if (n < 0 || n > 0x7E000000) goto done;                                  // lz4hc.c:810
     if (n == 0) { if (cap >= 1) { if (lane == 0) dst[0] = 0; ret = 1; } goto done; }
     {
-        for (int i = lane; i < (1 << HC_BUCKET_LOG); i += 32) t.head[i] = 0;
+        for (int i = lane; i < (1 << BL); i += 32) t.head[i] = 0;
         __syncwarp();
         const InGlobal in{src};
         const int mflimit = n - 12, matchlimit = n - 5;                      // lz4hc.c:566-567
@@ -109,14 +110,14 @@ lz4hc_compress_kernel(const uint8_t* __restrict__ src_base, const uint64_t* __re
         bool fail = false;
 
         while (ip <= mflimit) {
-            hc_insert(in, t, inserted, ip, lane); inserted = max(inserted, ip);
-            int dist, ml = hc_search(in, t, ip, matchlimit, lane, dist);
+            hc_insert<BL>(in, t, inserted, ip, lane); inserted = max(inserted, ip);
+            int dist, ml = hc_search<BL>(in, t, ip, matchlimit, lane, dist);
             if (ml < 4) { ip++; continue; }
             // lazy evaluation (the idea of lz4hc.c:599-732, simplified): prefer a strictly longer match
             // starting one byte later, a few times
             for (int k = 0; k < max_lazy && ip + 1 <= mflimit; k++) {
-                hc_insert(in, t, inserted, ip + 1, lane); inserted = max(inserted, ip + 1);
-                int d2; const int ml2 = hc_search(in, t, ip + 1, matchlimit, lane, d2);
+                hc_insert<BL>(in, t, inserted, ip + 1, lane); inserted = max(inserted, ip + 1);
+                int d2; const int ml2 = hc_search<BL>(in, t, ip + 1, matchlimit, lane, d2);
                 if (ml2 <= ml) break;
                 ip++; ml = ml2; dist = d2;
             }
@@ -150,15 +151,24 @@ done:
     if (lane == 0) result[b] = ret;
 }
 
+extern "C" { int b200lz4_hc_bucket_log = 11; }   // tuning knob: 11 = 2048 buckets (128 KiB), 10 = 1024 buckets (64 KiB, 3 CTAs/SM)
+
+template <int BL>
+static cudaError_t launch_hc(const BatchArgs& a, int level, cudaStream_t st)
+{
+    auto k = lz4hc_compress_kernel<BL>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hc_smem<BL>());
+    if (e != cudaSuccess) return e;
+    k<<<(unsigned)a.n, 32, hc_smem<BL>(), st>>>(a.src_base, a.src_off, a.src_len, a.dst_base, a.dst_off,
+                                              a.dst_cap, a.result, (uint32_t)a.n, level);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_compress_hc(const BatchArgs& a, int level, cudaStream_t st)
 {
     if (a.n == 0) return cudaSuccess;
     if (level < 1) level = 9;                                                 // LZ4HC_CLEVEL_DEFAULT, lz4hc.c:840
-    cudaError_t e = cudaFuncSetAttribute(lz4hc_compress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)HC_SMEM);
-    if (e != cudaSuccess) return e;
-    lz4hc_compress_kernel<<<(unsigned)a.n, 32, HC_SMEM, st>>>(a.src_base, a.src_off, a.src_len, a.dst_base, a.dst_off,
-                                                              a.dst_cap, a.result, (uint32_t)a.n, level);
-    return cudaGetLastError();
+    return b200lz4_hc_bucket_log == 10 ? launch_hc<10>(a, level, st) : launch_hc<11>(a, level, st);
 }
 
 } // namespace b200

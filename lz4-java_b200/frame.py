@@ -42,3 +42,75 @@ def decompress_frames(src, max_decoded: int) -> bytes:
     if r < 0:
         raise LZ4FrameError(int(r))
     return out[:r].tobytes()
+
+
+def compress_frame(src, block_size_code: int = 4, content_checksum=True, block_checksum=False, content_size=False) -> bytes:
+    """one LZ4 frame as LZ4FrameOutputStream writes it (LZ4FrameOutputStream.java:178-251), whole buffer at once"""
+    s = _view(src)
+    flags = (1 if content_checksum else 0) | (2 if block_checksum else 0) | (4 if content_size else 0)
+    L = N.lib()
+    cap = L.b200lz4f_compress_bound(len(s), block_size_code)
+    if cap == 0:
+        raise ValueError("block_size_code must be 4..7 (64 KiB .. 4 MiB)")
+    out = np.empty(cap, dtype=np.uint8)
+    r = L.b200lz4f_compress_host(s.ctypes.data, len(s), out.ctypes.data, cap, block_size_code, flags)
+    N.check(r)
+    if r < 0:
+        raise LZ4FrameError(int(r))
+    return out[:r].tobytes()
+
+
+# ---- lz4-java's private "LZ4Block" container (LZ4BlockOutputStream / LZ4BlockInputStream)
+def compress_lz4block(src, block_size: int = 1 << 16) -> bytes:
+    s = _view(src)
+    L = N.lib()
+    cap = L.b200lz4block_compress_bound(len(s), block_size)
+    if cap == 0:
+        raise ValueError("blockSize must be >= 64 and <= 32 MiB")            # LZ4BlockOutputStream.java:58-66
+    out = np.empty(cap, dtype=np.uint8)
+    r = L.b200lz4block_compress_host(s.ctypes.data, len(s), out.ctypes.data, cap, block_size)
+    N.check(r)
+    if r < 0:
+        raise LZ4FrameError(int(r))
+    return out[:r].tobytes()
+
+
+def decompress_lz4block(src, max_decoded: int) -> bytes:
+    s = _view(src)
+    out = np.empty(max(max_decoded, 1), dtype=np.uint8)
+    r = N.lib().b200lz4block_decompress_host(s.ctypes.data, len(s), out.ctypes.data, max_decoded)
+    N.check(r)
+    if r == -1:
+        raise EOFError("Stream ended prematurely")                           # LZ4BlockInputStream.java:197
+    if r < 0:
+        raise IOError("Stream is corrupted" if r == -2 else f"error {r}")    # LZ4BlockInputStream.java:203,...
+    return out[:r].tobytes()
+
+
+# ---- LZ4CompressorWithLength / LZ4DecompressorWithLength
+def compress_with_length(src) -> bytes:
+    s = _view(src)
+    cap = len(s) + len(s) // 255 + 16 + 4
+    out = np.empty(cap, dtype=np.uint8)
+    r = N.lib().b200lz4_compress_with_length(s.ctypes.data if len(s) else None, out.ctypes.data, len(s), cap)
+    N.check(r)
+    if r <= 0:
+        from .lz4 import LZ4Exception
+        raise LZ4Exception("maxDestLen is too small")
+    return out[:r].tobytes()
+
+
+def decompress_with_length(src) -> bytes:
+    s = _view(src)
+    from .lz4 import LZ4Exception
+    if len(s) < 4:
+        raise LZ4Exception("Error decoding offset 0 of input buffer")
+    n = N.lib().b200lz4_decompressed_length(s.ctypes.data)
+    if n < 0:
+        raise LZ4Exception("negative length")
+    out = np.empty(max(n, 1), dtype=np.uint8)
+    r = N.lib().b200lz4_decompress_with_length(s.ctypes.data, len(s), out.ctypes.data, n)
+    N.check(r)
+    if r < 0:
+        raise LZ4Exception("Error decoding offset " + str(-r) + " of input buffer")
+    return out[:n].tobytes()

@@ -82,6 +82,16 @@ class Port(_Lib):
         L.orc_frame_compress.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p]
         L.orc_frame_decompress.restype = C.c_int64
         L.orc_frame_decompress.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+        L.orc_lz4block_bound.restype = C.c_size_t
+        L.orc_lz4block_bound.argtypes = [C.c_size_t, C.c_int]
+        L.orc_lz4block_compress.restype = C.c_int64
+        L.orc_lz4block_compress.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p]
+        L.orc_lz4block_decompress.restype = C.c_int64
+        L.orc_lz4block_decompress.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+        L.orc_with_length_compress.restype = C.c_int
+        L.orc_with_length_compress.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.orc_with_length_decompress.restype = C.c_int
+        L.orc_with_length_decompress.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.orc_cpu_bench.restype = C.c_double
         L.orc_cpu_bench.argtypes = [C.c_int, C.c_void_p] + [C.c_void_p] * 7 + [C.c_size_t, C.c_int, C.c_int, C.POINTER(C.c_double)]
 
@@ -147,6 +157,34 @@ class Port(_Lib):
         d = np.empty(max(cap, 1), dtype=np.uint8)
         r = self.L.orc_frame_decompress(_ptr(s), len(s), _ptr(d), cap)
         return r, d[: max(r, 0)].tobytes()
+
+    # ---- lz4-java's own containers
+    def lz4block_compress(self, src, block_size=65536) -> bytes:
+        s = _as_u8(src)
+        d = np.empty(self.L.orc_lz4block_bound(len(s), block_size) + 64, dtype=np.uint8)
+        scratch = np.empty(self.compress_bound(block_size) + 64, dtype=np.uint8)
+        r = self.L.orc_lz4block_compress(_ptr(s), len(s), _ptr(d), block_size, _ptr(scratch))
+        return d[:r].tobytes()
+
+    def lz4block_decompress(self, src, cap: int):
+        s = _as_u8(src)
+        d = np.empty(max(cap, 1), dtype=np.uint8)
+        r = self.L.orc_lz4block_decompress(_ptr(s), len(s), _ptr(d), cap)
+        return r, d[: max(r, 0)].tobytes()
+
+    def with_length_compress(self, src) -> bytes:
+        s = _as_u8(src)
+        cap = self.compress_bound(len(s)) + 4
+        d = np.empty(cap, dtype=np.uint8)
+        r = self.L.orc_with_length_compress(_ptr(s), _ptr(d), len(s), cap)
+        return d[:r].tobytes()
+
+    def with_length_decompress(self, src, cap: int):
+        s = np.concatenate([_as_u8(src), np.zeros(cap + cap // 255 + 64, dtype=np.uint8)])
+        d = np.zeros(max(cap, 1), dtype=np.uint8)
+        r = self.L.orc_with_length_decompress(_ptr(s), _ptr(d), cap)
+        n = int.from_bytes(bytes(s[:4]), "little") if r >= 0 else 0
+        return r, d[:n].tobytes()
 
     # ---- function addresses for the pthread harness
     def fn_addr(self, op: str) -> int:

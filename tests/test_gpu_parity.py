@@ -390,3 +390,42 @@ def test_frame_batch_decoder(b200, port):
     with pytest.raises(b200.LZ4FrameError) as e:
         b200.decompress_frames(good, len(b) - 1)
     assert e.value.code == -9
+
+
+def test_frame_writer_and_lz4java_containers(b200, port):
+    """(f)-2..4: frames / LZ4Block streams / length-prefixed blocks WRITTEN on the GPU path are read by the CPU
+    restatements (and by the reference's LZ4F_decompress when available), and vice versa"""
+    from oracle import oracle as O
+    try:
+        ref = O.Ref()
+    except (FileNotFoundError, OSError):
+        ref = None
+    rng = random.Random(12)
+    for n in (0, 1, 100, 65536, 65537, 300000, 3 << 20):
+        data = port.datagen(n, 0.5, 0.0, n & 0xFF).tobytes()
+        for bs, cc, bc, cs in ((4, True, False, False), (5, True, True, True), (7, False, False, False), (6, False, True, False)):
+            f = b200.compress_frame(data, bs, cc, bc, cs)
+            r, out = port.frame_decompress(f, n + 8)
+            assert r == n and out == data, (n, bs)
+            if ref is not None:
+                r, out = ref.frame_decompress(f, n + 8)
+                assert r == n and out == data, ("LZ4F_decompress", n, bs)
+            assert b200.decompress_frames(f, n + 8) == data
+        for blk in (64, 4096, 65536, 1 << 20):
+            blob = b200.compress_lz4block(data, blk)
+            r, out = port.lz4block_decompress(blob, n)
+            assert r == n and out == data, (n, blk)
+            assert b200.decompress_lz4block(port.lz4block_compress(data, blk), n) == data
+            assert b200.decompress_lz4block(blob + blob, 2 * n) == data + data
+        wl = b200.compress_with_length(data)
+        assert port.with_length_decompress(wl, n) == (len(wl), data)
+        assert b200.decompress_with_length(port.with_length_compress(data)) == data
+    noise = rng.randbytes(200000)                                   # stored (raw) blocks
+    assert port.frame_decompress(b200.compress_frame(noise, 4), len(noise))[1] == noise
+    assert port.lz4block_decompress(b200.compress_lz4block(noise, 65536), len(noise))[1] == noise
+    good = port.lz4block_compress(port.datagen(70000, 0.5, 0.0, 1).tobytes(), 65536)
+    bad = bytearray(good); bad[50] ^= 0x41
+    with pytest.raises(IOError):
+        b200.decompress_lz4block(bytes(bad), 70000)
+    with pytest.raises(EOFError):
+        b200.decompress_lz4block(good[:100], 70000)

@@ -119,3 +119,27 @@ def test_ref_differential_frames(port, ref):
     assert r == len(a) + len(b) and out == a + b
     bad = bytearray(port.frame_compress(b, 4, 1)); bad[-1] ^= 1          # content checksum mismatch
     assert port.frame_decompress(bytes(bad), len(b))[0] == -7
+
+
+def test_container_restatements_roundtrip(port):
+    """LZ4Block container and length-prefixed blocks: the restatements invert themselves and reject corruption"""
+    rng = random.Random(8)
+    for n in (0, 1, 63, 64, 1000, 65536, 65537, 300000):
+        data = port.datagen(n, 0.5, 0.0, 3).tobytes()
+        for bs in (64, 4096, 65536, 1 << 20):
+            blob = port.lz4block_compress(data, bs)
+            assert blob[:8] == b"LZ4Block" and blob[-21:-13] == b"LZ4Block"
+            r, out = port.lz4block_decompress(blob, n)
+            assert r == n and out == data, (n, bs)
+            r, out = port.lz4block_decompress(blob + blob, 2 * n)              # concatenated streams (LZ4BlockStreamingTest.java:309-348)
+            assert r == 2 * n and out == data + data
+        wl = port.with_length_compress(data)
+        assert int.from_bytes(wl[:4], "little") == n
+        r, out = port.with_length_decompress(wl, n)
+        assert r == len(wl) and out == data
+    noise = rng.randbytes(5000)
+    blob = port.lz4block_compress(noise, 4096)
+    assert blob[8] & 0xF0 == 0x10                                               # incompressible -> RAW method
+    bad = bytearray(port.lz4block_compress(port.datagen(5000, 0.5, 0.0, 1).tobytes(), 4096)); bad[40] ^= 0x55
+    assert port.lz4block_decompress(bytes(bad), 5000)[0] == -2
+    assert port.lz4block_decompress(blob[:30], 5000)[0] == -1

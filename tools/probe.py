@@ -95,6 +95,7 @@ def hc_probe():
     ccap = torch.full((nblk,), bound, device=dev, dtype=torch.int32)
     comp = torch.zeros(nblk * stride, device=dev, dtype=torch.uint8)
     clen = torch.zeros(nblk, device=dev, dtype=torch.int32)
+    ctypes.c_int.in_dll(L._native.lib(), "b200lz4_hc_bucket_log").value = int(os.environ.get("HC_BL", 11))
     t, med = timeit(lambda: L.batch.compress_hc_batch_dev(src, soff, slen, comp, coff, ccap, clen, 9), iters=2, warm=1)
     N = nblk * bs; C = int(clen.sum().item())
     ref_c = sum(len(chk.compress_hc(host[i * bs:(i + 1) * bs], 9)) for i in range(4)) if hasattr(chk, "compress_hc") else 0
