@@ -1,0 +1,141 @@
+"""Secondary configurations of BASELINE.json (configs[2..4]) — measured for the record, not bench lines.
+
+  config 3: LZ4 frame decode (4 MiB independent blocks + XXH32 content checksum), device-resident and end to end
+  config 4: LZ4 HC level 9, 256 KiB blocks: GiB/s + ratio vs LZ4_compress_HC(9)
+  config 5: XXH64 / XXH32 over many 4 KiB buffers, GB/s vs the measured HBM peak
+Sizes are scaled to one GPU and a few seconds; every number is checked against the CPU oracle on a sample."""
+import ctypes as C
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+import lz4java_b200 as L
+from oracle import oracle as O
+
+GIB = float(1 << 30)
+
+
+def timeit(fn, iters=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) / 1e3)
+    return min(ts)
+
+
+def config5(chk, out):
+    dev = torch.device("cuda:0")
+    n = int(os.environ.get("XXH_BUFS", 8 << 20))                   # 8 Mi x 4 KiB = 32 GiB
+    data = torch.empty(n * 4096, dtype=torch.uint8, device=dev)
+    base = torch.randint(0, 256, (1 << 28,), dtype=torch.uint8, device=dev)
+    for i in range(0, n * 4096, 1 << 28):
+        data[i:i + (1 << 28)] = base[: min(1 << 28, n * 4096 - i)]
+    idx = torch.arange(n, device=dev, dtype=torch.int64)
+    v = data.view(n, 4096)
+    for k in range(4):
+        v[:, k] ^= ((idx >> (8 * k)) & 0xFF).to(torch.uint8)
+    off = idx * 4096
+    ln = torch.full((n,), 4096, device=dev, dtype=torch.int32)
+    o64 = torch.zeros(n, device=dev, dtype=torch.int64)
+    o32 = torch.zeros(n, device=dev, dtype=torch.int32)
+    t64 = timeit(lambda: L.batch.xxh64_batch_dev(data, off, ln, o64, 0))
+    t32 = timeit(lambda: L.batch.xxh32_batch_dev(data, off, ln, o32, 0x9747B28C))
+    for k in (0, 1, n // 3, n - 1):
+        b = data[k * 4096:(k + 1) * 4096].cpu().numpy()
+        assert (int(o64[k].item()) & (2 ** 64 - 1)) == chk.xxh64(b, 0)
+        assert (int(o32[k].item()) & 0xFFFFFFFF) == chk.xxh32(b, 0x9747B28C)
+    peak = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")) else 6650.0
+    out["config5_xxh"] = {"buffers": n, "buffer_bytes": 4096, "xxh64_GBps": (n * 4104) / t64 / 1e9, "xxh32_GBps": (n * 4100) / t32 / 1e9,
+                          "xxh64_frac_of_measured_hbm": (n * 4104) / t64 / 1e9 / peak, "xxh32_frac_of_measured_hbm": (n * 4100) / t32 / 1e9 / peak,
+                          "verified": "4 sampled buffers bit-exact vs CPU checker"}
+    del data, base
+
+
+def config3(chk, out):
+    dev = torch.device("cuda:0")
+    lib = L._native.lib()
+    nframes = int(os.environ.get("FRAMES", 32)); fsize = 64 << 20   # 32 x 64 MiB = 2 GiB of content, 4 MiB blocks
+    one = chk.datagen(fsize, 0.5, 0.0, 3)
+    t0 = time.time()
+    frame = np.frombuffer(chk.frame_compress(one, 7, 1), dtype=np.uint8)
+    host = np.concatenate([frame] * nframes)
+    print(f"  built {nframes} frames of {fsize >> 20} MiB ({len(host) / GIB:.2f} GiB compressed) in {time.time() - t0:.1f}s", flush=True)
+    slot = C.c_uint64(); err = C.c_int()
+    index = lib.b200lz4f_index_create(host.ctypes.data, len(host), C.byref(slot), C.byref(err))
+    assert index, err.value
+    d_src = torch.from_numpy(host).to(dev)
+    d_slots = torch.empty(slot.value + 16, dtype=torch.uint8, device=dev)
+    foff = np.zeros(nframes, dtype=np.uint64); flen = np.zeros(nframes, dtype=np.uint64)
+    st = torch.cuda.current_stream().cuda_stream
+
+    def run():
+        r = lib.b200lz4f_decode_dev(index, d_src.data_ptr(), d_slots.data_ptr(), foff.ctypes.data, flen.ctypes.data, None, st)
+        assert r == nframes * fsize, r
+    t = timeit(run, iters=3, warm=1)
+    got = d_slots[int(foff[1]):int(foff[1]) + fsize].cpu().numpy()
+    assert (got == one).all()
+    total = nframes * fsize
+    # end to end with host buffers
+    outbuf = np.empty(total, dtype=np.uint8)
+    t1 = time.perf_counter()
+    r = lib.b200lz4f_decompress_host(host.ctypes.data, len(host), outbuf.ctypes.data, total)
+    te = time.perf_counter() - t1
+    assert r == total and (outbuf[:fsize] == one).all() and (outbuf[-fsize:] == one).all()
+    out["config3_frame_decode"] = {"frames": nframes, "frame_MiB": fsize >> 20, "block": "4 MiB independent, content checksum",
+                                   "device_resident_GiBps": total / t / GIB, "end_to_end_host_GiBps": total / te / GIB,
+                                   "blocks": int(lib.b200lz4f_index_blocks(index)),
+                                   "note": "device time includes header/content XXH32 verification and two host syncs for sizes/checksums; "
+                                           "content hash = one lane per frame (XXH32 is a serial chain per frame)"}
+    lib.b200lz4f_index_free(index)
+
+
+def config4(chk, out):
+    dev = torch.device("cuda:0")
+    nblk = int(os.environ.get("HC_NBLK", 2048)); bs = 262144
+    base_n = min(nblk, 256)
+    host = chk.datagen(base_n * bs, 0.5, 0.0, 4)
+    src = torch.from_numpy(host).to(dev).repeat((nblk + base_n - 1) // base_n)[: nblk * bs].contiguous()
+    bound = L.max_compressed_length(bs); stride = (bound + 15) // 16 * 16
+    soff = torch.arange(nblk, device=dev, dtype=torch.int64) * bs
+    slen = torch.full((nblk,), bs, device=dev, dtype=torch.int32)
+    coff = torch.arange(nblk, device=dev, dtype=torch.int64) * stride
+    ccap = torch.full((nblk,), bound, device=dev, dtype=torch.int32)
+    comp = torch.zeros(nblk * stride, device=dev, dtype=torch.uint8)
+    clen = torch.zeros(nblk, device=dev, dtype=torch.int32)
+    res = {}
+    for bl in (11, 10):
+        C.c_int.in_dll(L._native.lib(), "b200lz4_hc_bucket_log").value = bl
+        t = timeit(lambda: L.batch.compress_hc_batch_dev(src, soff, slen, comp, coff, ccap, clen, 9), iters=2, warm=1)
+        csum = int(clen.sum().item())
+        res[f"buckets_{1 << bl}"] = {"GiBps": nblk * bs / t / GIB, "ratio": nblk * bs / csum}
+    C.c_int.in_dll(L._native.lib(), "b200lz4_hc_bucket_log").value = 11
+    ref_c = sum(len(chk.compress_hc(host[i * bs:(i + 1) * bs], 9)) for i in range(8)) if hasattr(chk, "compress_hc") else None
+    t0 = time.perf_counter()
+    if hasattr(chk, "compress_hc"):
+        for i in range(8):
+            chk.compress_hc(host[i * bs:(i + 1) * bs], 9)
+    tc = time.perf_counter() - t0
+    out["config4_hc9"] = {"blocks": nblk, "block_bytes": bs, **res,
+                          "reference_hc9_ratio_first8": (8 * bs / ref_c) if ref_c else None,
+                          "reference_hc9_single_thread_MBps": (8 * bs / tc / 1e6) if ref_c else None}
+
+
+if __name__ == "__main__":
+    chk = O.best_available()
+    out = {"gpu": torch.cuda.get_device_name(0)}
+    for name, fn in (("config5", config5), ("config3", config3), ("config4", config4)):
+        if os.environ.get("ONLY") and os.environ["ONLY"] != name:
+            continue
+        print("running", name, flush=True)
+        fn(chk, out)
+        torch.cuda.empty_cache()
+    print(json.dumps(out, indent=1))

@@ -1,0 +1,5 @@
+ulimit -c 0
+timeout 900 python tools/bench_configs.py > gpurun_out/configs.json 2> gpurun_out/configs.err; tail -40 gpurun_out/configs.json; tail -5 gpurun_out/configs.err
+timeout 900 python bench.py --blocks 262144 --steps 4 --warmup 3 > gpurun_out/bench25.json 2> gpurun_out/bench25.err; tail -3 gpurun_out/bench25.err
+python -c "
+import json; d=json.load(open('gpurun_out/bench25.json')); print({k:d[k] for k in ('value','compress_gibs','decompress_gibs','ratio','e2e')}); print(d['cpu_baseline'])"
