@@ -1,4 +1,4 @@
-// lz4hc_compress.cu — batch LZ4 HC block compression (level 9 class), one independent block per warp.
+// lz4hc_compress.cu — batch LZ4 HC block compression (level 9 class), one independent block per 4-warp CTA.
 //
 // Replaces the reference's LZ4_compress_HC (lz4hc.c:958-973 -> 800-861 -> LZ4HC_compress_hashChain
 // 553-788, match finder LZ4HC_InsertAndGetWiderMatch 239-447) as called from the JNI shim
@@ -77,8 +77,13 @@ __device__ __forceinline__ int hc_search(const In& in, const HcTable& t, int p, 
     return bml;
 }
 
+// One block per CTA of 4 warps.  Lazy evaluation wants the best match at p, p+1, p+2, ... — four
+// consecutive positions are searched CONCURRENTLY, one per warp (each search is itself 32 candidates
+// wide), then every thread takes the same decision from the four results: first position with a match,
+// then move right while the next position's match is strictly longer (the idea of lz4hc.c:599-732,
+// simplified).  Stretches without matches advance four positions per round.
 template <int BL>
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(128)
 lz4hc_compress_kernel(const uint8_t* __restrict__ src_base, const uint64_t* __restrict__ src_off,
                       const int32_t* __restrict__ src_len,
                       uint8_t* __restrict__ dst_base, const uint64_t* __restrict__ dst_off,
@@ -88,54 +93,74 @@ lz4hc_compress_kernel(const uint8_t* __restrict__ src_base, const uint64_t* __re
     HcTable t;
     t.ring = reinterpret_cast<uint16_t*>(smem_raw);
     t.head = reinterpret_cast<uint32_t*>(smem_raw + (size_t(2) << BL) * HC_WAYS);
+    int* s_res = reinterpret_cast<int*>(smem_raw + hc_smem<BL>());              // [4][2] (ml, dist), [8] = fail flag
 
     const uint32_t b = blockIdx.x;
     if (b >= nblocks) return;
-    const int lane = lane_id();
+    const int lane = lane_id(), warp = threadIdx.x >> 5, tid = threadIdx.x;
     const uint8_t* __restrict__ src = src_base + src_off[b];
     uint8_t* __restrict__ dst = dst_base + dst_off[b];
     const int n = src_len[b];
     const int cap = dst_cap[b];
-    int ret = 0;
 
-    if (n < 0 || n > 0x7E000000) goto done;                                  // lz4hc.c:810
-    if (n == 0) { if (cap >= 1) { if (lane == 0) dst[0] = 0; ret = 1; } goto done; }
-    {
-        for (int i = lane; i < (1 << BL); i += 32) t.head[i] = 0;
-        __syncwarp();
-        const InGlobal in{src};
-        const int mflimit = n - 12, matchlimit = n - 5;                      // lz4hc.c:566-567
-        const int max_lazy = level >= 9 ? 3 : (level >= 4 ? 1 : 0);          // how far a better later match is chased
-        int op = 0, anchor = 0, ip = 0, inserted = 0;
-        bool fail = false;
+    if (n < 0 || n > 0x7E000000) { if (tid == 0) result[b] = 0; return; }                        // lz4hc.c:810
+    if (n == 0) { if (tid == 0) { if (cap >= 1) dst[0] = 0; result[b] = cap >= 1 ? 1 : 0; } return; }
 
-        while (ip <= mflimit) {
-            hc_insert<BL>(in, t, inserted, ip, lane); inserted = max(inserted, ip);
-            int dist, ml = hc_search<BL>(in, t, ip, matchlimit, lane, dist);
-            if (ml < 4) { ip++; continue; }
-            // lazy evaluation (the idea of lz4hc.c:599-732, simplified): prefer a strictly longer match
-            // starting one byte later, a few times
-            for (int k = 0; k < max_lazy && ip + 1 <= mflimit; k++) {
-                hc_insert<BL>(in, t, inserted, ip + 1, lane); inserted = max(inserted, ip + 1);
-                int d2; const int ml2 = hc_search<BL>(in, t, ip + 1, matchlimit, lane, d2);
-                if (ml2 <= ml) break;
-                ip++; ml = ml2; dist = d2;
-            }
-            int ms = ip, mc = ip - dist;
-            {   // catch-up over pending literals (LZ4HC_countBack, lz4hc.c:146-158), at most 8 bytes
-                const int backroom = min(min(ms - anchor, mc), 8);
-                const bool eq = lane < backroom && in.ld1(ms - 1 - lane) == in.ld1(mc - 1 - lane);
-                const unsigned e = __ballot_sync(B200_FULL, eq);
-                const int back = __ffs(~e) - 1;
-                ms -= back; ml += back;
-            }
-            Seq q{anchor, ms, dist, ml};
-            uint32_t litv = 0;
-            if (lane < ms - anchor && ms - anchor <= 32) litv = in.ld1(anchor + lane);
-            if (!emit_sequence(in, q, litv, dst, op, cap, lane)) { fail = true; break; }
-            ip = anchor = ms + ml;
+    for (int i = tid; i < (1 << BL); i += 128) t.head[i] = 0;
+    if (tid == 0) s_res[8] = 0;
+    const InGlobal in{src};
+    const int mflimit = n - 12, matchlimit = n - 5;                                              // lz4hc.c:566-567
+    const int max_lazy = level >= 9 ? 3 : (level >= 4 ? 1 : 0);
+    int op = 0;                     // warp 0 only
+    int anchor = 0, ip = 0, inserted = 0;
+    __syncthreads();
+
+    while (ip <= mflimit) {
+        // every position below ip+4 goes into its bucket ring (LZ4HC_Insert, lz4hc.c:120-141), 128 per pass
+        const int ins_end = min(ip + 4, mflimit + 1);
+        for (int p = inserted + tid; p < ins_end; p += 128) {
+            const uint32_t h = hc_hash<BL>(in.ld4(p));
+            const uint32_t slot = atomicAdd(&t.head[h], 1u) & (HC_WAYS - 1);
+            t.ring[h * HC_WAYS + slot] = uint16_t(p);
         }
-        if (!fail) {
+        inserted = max(inserted, ins_end);
+        __syncthreads();
+        {
+            const int p = ip + warp;
+            int dist = 0, ml = 0;
+            if (p <= mflimit) ml = hc_search<BL>(in, t, p, matchlimit, lane, dist);
+            if (lane == 0) { s_res[2 * warp] = ml; s_res[2 * warp + 1] = dist; }
+        }
+        __syncthreads();
+        int cur = -1;
+        #pragma unroll
+        for (int k = 3; k >= 0; k--) if (s_res[2 * k] >= 4) cur = k;
+        const bool failed = s_res[8] != 0;
+        __syncthreads();                                            // results consumed before the next round overwrites them
+        if (failed) break;
+        if (cur < 0) { ip += 4; continue; }
+        for (int k = 0; k < max_lazy && cur < 3; k++) {
+            if (s_res[2 * (cur + 1)] > s_res[2 * cur]) cur++; else break;
+        }
+        int ms = ip + cur, ml = s_res[2 * cur];
+        const int dist = s_res[2 * cur + 1];
+        if (warp == 0) {
+            const int mc = ms - dist;
+            const int backroom = min(min(ms - anchor, mc), 8);      // LZ4HC_countBack, lz4hc.c:146-158 (at most 8 bytes)
+            const bool eq = lane < backroom && in.ld1(ms - 1 - lane) == in.ld1(mc - 1 - lane);
+            const unsigned e = __ballot_sync(B200_FULL, eq);
+            const int back = __ffs(~e) - 1;
+            Seq q{anchor, ms - back, dist, ml + back};
+            uint32_t litv = 0;
+            if (lane < q.ms - anchor && q.ms - anchor <= 32) litv = in.ld1(anchor + lane);
+            if (!emit_sequence(in, q, litv, dst, op, cap, lane)) { if (lane == 0) s_res[8] = 1; }
+        }
+        ip = anchor = ms + ml;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        int ret = 0;
+        if (s_res[8] == 0) {
             const int lit = n - anchor;                                       // last literals (lz4hc.c:737-770)
             const int lhdr = lit >= 15 ? (lit - 15) / 255 + 1 : 0;
             if ((long long)op + 1 + lhdr + lit <= cap) {
@@ -146,9 +171,8 @@ lz4hc_compress_kernel(const uint8_t* __restrict__ src_base, const uint64_t* __re
                 ret = op + lit;
             }
         }
+        if (lane == 0) result[b] = ret;
     }
-done:
-    if (lane == 0) result[b] = ret;
 }
 
 extern "C" { int b200lz4_hc_bucket_log = 11; }   // tuning knob: 11 = 2048 buckets (128 KiB), 10 = 1024 buckets (64 KiB, 3 CTAs/SM)
@@ -157,9 +181,9 @@ template <int BL>
 static cudaError_t launch_hc(const BatchArgs& a, int level, cudaStream_t st)
 {
     auto k = lz4hc_compress_kernel<BL>;
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hc_smem<BL>());
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hc_smem<BL>() + 64);
     if (e != cudaSuccess) return e;
-    k<<<(unsigned)a.n, 32, hc_smem<BL>(), st>>>(a.src_base, a.src_off, a.src_len, a.dst_base, a.dst_off,
+    k<<<(unsigned)a.n, 128, hc_smem<BL>() + 64, st>>>(a.src_base, a.src_off, a.src_len, a.dst_base, a.dst_off,
                                               a.dst_cap, a.result, (uint32_t)a.n, level);
     return cudaGetLastError();
 }
