@@ -29,6 +29,9 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# the host-buffer pipeline runs 3 streams per calling thread; with the default 8 hardware queues two threads'
+# H2D / kernel / D2H chains pick up false dependencies (measured: 172 vs 123 ms per overlapped call)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 BLOCK = 65536
 METRIC = "lz4_fast_compress_plus_decompress_64KiB_blocks"
@@ -401,9 +404,13 @@ def run_e2e(args, L, dev, host, rank, world):
     q_free.put(0); q_free.put(1)
     state = {"err": None, "last": None}
 
+    go = threading.Event(); ready = threading.Event()
+
     def producer():
         try:
             L._native.check(lib.b200lz4_set_device(local))
+            B.compress_fast_compact_host(src, soff, slen, comp[0], BLOCK)    # untimed: this thread's streams + staging buffers
+            ready.set(); go.wait()
             for k in range(args.steps):
                 buf = q_free.get()
                 ooff, olen, total = B.compress_fast_compact_host(src, soff, slen, comp[buf], BLOCK)
@@ -412,11 +419,13 @@ def run_e2e(args, L, dev, host, rank, world):
             state["err"] = e
         q_full.put(None)
 
+    th = threading.Thread(target=producer)
+    th.start()
+    ready.wait()
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
-    th = threading.Thread(target=producer)
-    th.start()
+    go.set()
     while True:
         item = q_full.get()
         if item is None:

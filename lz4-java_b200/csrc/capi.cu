@@ -73,7 +73,8 @@ struct Slot {
 };
 
 static constexpr int    NSLOTS = 3;
-static constexpr size_t CHUNK_SPAN = size_t(256) << 20;    // bytes of src (and of dst) per pipeline chunk: >= 4096 64-KiB blocks,
+static size_t chunk_span_init() { const char* e = getenv("B200LZ4_CHUNK_MB"); size_t mb = e ? (size_t)atol(e) : 256; if (mb < 1) mb = 1; return mb << 20; }
+static const size_t CHUNK_SPAN = chunk_span_init();    // bytes of src (and of dst) per pipeline chunk: >= 4096 64-KiB blocks,
                                                            // i.e. at least two full waves of warps on 148 SMs per launch
 static constexpr size_t CHUNK_BLOCKS = 1 << 16;
 

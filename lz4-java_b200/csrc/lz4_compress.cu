@@ -391,7 +391,7 @@ static cudaError_t launch_v2(const BatchArgs& a, cudaStream_t st)
 // records) over.  Same parse, same output bytes as algo 2.
 struct SeqRec { int anchor, ms, dist, ml; };
 
-template <int HASH_LOG, bool U16>
+template <int HASH_LOG, bool U16, bool SPARSE>
 __global__ void __launch_bounds__(64)
 lz4_compress_fast3_kernel(const uint8_t* __restrict__ src_base, const uint64_t* __restrict__ src_off,
                           const int32_t* __restrict__ src_len,
@@ -459,7 +459,9 @@ lz4_compress_fast3_kernel(const uint8_t* __restrict__ src_base, const uint64_t* 
                 for (int j = 0; j < 4; j++) {
                     const int p = p0 + j;
                     const bool valid = p >= 0 && p <= mflimit;
-                    if (valid) table[h[j]] = Entry(p);
+                    // SPARSE: only one position in four is published (every position is still probed); a
+                    // half-size table then keeps about the same history (ratio -2..-5 %, twice the warps/SM)
+                    if (valid && (!SPARSE || j == 0)) table[h[j]] = Entry(p);
                     plaus[j] = valid && cand[j] < p && (U16 || p - cand[j] <= 65535);
                 }
                 uint32_t cseq[4];
@@ -581,11 +583,11 @@ lz4_compress_fast3_kernel(const uint8_t* __restrict__ src_base, const uint64_t* 
     }
 }
 
-template <int HASH_LOG, bool U16>
+template <int HASH_LOG, bool U16, bool SPARSE>
 static cudaError_t launch_v3(const BatchArgs& a, cudaStream_t st)
 {
     const size_t smem = ((U16 ? 2u : 4u) << HASH_LOG) + 512 + 1024 + 32 + 16;
-    auto k = lz4_compress_fast3_kernel<HASH_LOG, U16>;
+    auto k = lz4_compress_fast3_kernel<HASH_LOG, U16, SPARSE>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -612,6 +614,7 @@ static cudaError_t launch_variant(const BatchArgs& a, cudaStream_t st)
 extern "C" {
 int b200lz4_compress_hash_log = 13;   // 13 = the reference's table size for <64 KiB blocks (lz4.c:756-762)
 int b200lz4_compress_stage = 0;       // 1 = stage <=64 KiB blocks in shared memory via TMA (v1 parser only)
+int b200lz4_compress_sparse = 0;      // 1 = publish one position in four (pairs with hash_log 12: the 'fast' operating point)
 int b200lz4_compress_algo = 3;        // 3 = decoupled, two-warp pipeline (default); 2 = decoupled, one warp; 1 = coupled warp parser
 }
 
@@ -620,9 +623,9 @@ cudaError_t launch_compress_fast(const BatchArgs& a, int max_src_len, cudaStream
     if (a.n == 0) return cudaSuccess;
     const bool u16 = max_src_len > 0 && max_src_len <= 65536;
     if (b200lz4_compress_algo == 3 && !b200lz4_compress_stage) {
-        if (!u16) return launch_v3<12, false>(a, st);
-        if (b200lz4_compress_hash_log == 12) return launch_v3<12, true>(a, st);
-        return launch_v3<13, true>(a, st);
+        if (!u16) return launch_v3<12, false, false>(a, st);
+        if (b200lz4_compress_hash_log == 12) return b200lz4_compress_sparse ? launch_v3<12, true, true>(a, st) : launch_v3<12, true, false>(a, st);
+        return b200lz4_compress_sparse ? launch_v3<13, true, true>(a, st) : launch_v3<13, true, false>(a, st);
     }
     if (b200lz4_compress_algo == 2 && !b200lz4_compress_stage) {
         if (!u16) return launch_v2<12, false>(a, st);

@@ -45,13 +45,15 @@ def main():
     lib = L._native.lib()
     variants = os.environ.get("VARIANTS", "13:0:3,12:0:3,13:0:2,12:0:2,13:0:1")
     for v in variants.split(","):
-        hl, stage, algo = (int(x) for x in (v.split(":") + ["3"])[:3])
+        parts = v.split(":") + ["3", "0"]
+        hl, stage, algo, sparse = int(parts[0]), int(parts[1]), int(parts[2]), int(parts[3])
+        ctypes.c_int.in_dll(lib, "b200lz4_compress_sparse").value = sparse
         ctypes.c_int.in_dll(lib, "b200lz4_compress_hash_log").value = hl
         ctypes.c_int.in_dll(lib, "b200lz4_compress_stage").value = stage
         ctypes.c_int.in_dll(lib, "b200lz4_compress_algo").value = algo
         t, med = timeit(lambda: B.compress_fast_batch_dev(src, soff, slen, comp, coff, ccap, clen, bs))
         C = int(clen.sum().item())
-        print(f"compress hl={hl} stage={stage} algo={algo}: {N/t/2**30:.1f} GiB/s best ({N/med/2**30:.1f} med)  ratio {N/C:.3f}  hbm {(N+C)/t/1e9:.0f} GB/s", flush=True)
+        print(f"compress hl={hl} stage={stage} algo={algo} sparse={sparse}: {N/t/2**30:.1f} GiB/s best ({N/med/2**30:.1f} med)  ratio {N/C:.3f}  hbm {(N+C)/t/1e9:.0f} GB/s", flush=True)
     t, med = timeit(lambda: B.decompress_safe_batch_dev(comp, coff, clen, out, soff, slen, res))
     ok = bool((res == bs).all().item()) and bool(torch.equal(out, src))
     print(f"decompress_safe: {N/t/2**30:.1f} GiB/s best ({N/med/2**30:.1f} med) ok={ok}  hbm {(N+C)/t/1e9:.0f} GB/s", flush=True)
