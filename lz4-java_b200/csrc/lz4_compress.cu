@@ -272,6 +272,8 @@ lz4_compress_fast2_kernel(const uint8_t* __restrict__ src_base, const uint64_t* 
             seq[0] = w0; seq[1] = __funnelshift_r(w0, w1, 8); seq[2] = __funnelshift_r(w0, w1, 16); seq[3] = __funnelshift_r(w0, w1, 24);
             #pragma unroll
             for (int j = 0; j < 4; j++) { h[j] = (seq[j] * 2654435761u) >> (32 - HASH_LOG); cand[j] = table[h[j]]; }
+            __syncwarp();      // every lookup of the chunk precedes every insert.  Lanes whose sequences hash alike then
+                               // store to the same slot: any winner is a valid (earlier) position, so the race is benign
             #pragma unroll
             for (int j = 0; j < 4; j++) {
                 const int p = p0 + j;
@@ -455,6 +457,7 @@ lz4_compress_fast3_kernel(const uint8_t* __restrict__ src_base, const uint64_t* 
                 seq[0] = w0; seq[1] = __funnelshift_r(w0, w1, 8); seq[2] = __funnelshift_r(w0, w1, 16); seq[3] = __funnelshift_r(w0, w1, 24);
                 #pragma unroll
                 for (int j = 0; j < 4; j++) { h[j] = (seq[j] * 2654435761u) >> (32 - HASH_LOG); cand[j] = table[h[j]]; }
+                __syncwarp();  // every lookup of the chunk precedes every insert (same-slot stores: any winner is a valid position)
                 #pragma unroll
                 for (int j = 0; j < 4; j++) {
                     const int p = p0 + j;
