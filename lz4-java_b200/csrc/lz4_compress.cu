@@ -26,6 +26,7 @@
 #include "kernels.h"
 #include "lz4_emit.cuh"
 #include <type_traits>
+#include <algorithm>
 
 namespace b200 {
 
@@ -599,6 +600,298 @@ static cudaError_t launch_v3(const BatchArgs& a, cudaStream_t st)
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------
+// Three-kernel pipeline (algo 4): the three phases of the decoupled parser as three launches over a
+// sub-batch, each shaped for what it does, with the per-position state in a global scratch arena:
+//   K1 lookup   one warp per block, hash table in shared memory (13 warps/SM): phase AB only — distances
+//               (u16 per position) and hit masks go to the arena, fully coalesced.
+//   K2 walk     ONE THREAD per block (32 blocks per warp, no shared memory, 64 warps/SM): the serial greedy
+//               walk is scalar work, so it runs as scalar work at 32x the multiplicity; match extension is
+//               per-lane up to 32 bytes, longer matches are finished cooperatively by the whole warp.
+//               Output: one 8-byte record per sequence.
+//   K3 layout   one warp per block (64 warps/SM): prefix sums of sequence sizes, 32 tokens/offsets per
+//               instruction, cooperative literal copies, last literals, result.
+// Same parse and same bytes as algos 2/3.  The arena costs extra memory traffic (it does not fit L2);
+// DESIGN.md discusses that trade.
+static constexpr int K4_DIST_STRIDE = 65536 + 128;     // u16 entries per block, indexed by aligned-view byte
+static constexpr int K4_MASK_STRIDE = 2064;            // u32 words per block
+static constexpr int K4_REC_STRIDE  = 16400;           // uint2 records per block (>= 65536/4 + slack)
+
+template <int HASH_LOG, bool SPARSE>
+__global__ void __launch_bounds__(32)
+lz4c4_lookup_kernel(const uint8_t* __restrict__ src_base, const uint64_t* __restrict__ src_off,
+                    const int32_t* __restrict__ src_len, uint32_t first, uint32_t nsb,
+                    uint16_t* __restrict__ g_dist, uint32_t* __restrict__ g_mask)
+{
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    uint16_t* table = reinterpret_cast<uint16_t*>(smem_raw);
+    const uint32_t sb = blockIdx.x;
+    if (sb >= nsb) return;
+    const int lane = lane_id();
+    const uint8_t* __restrict__ src = src_base + src_off[first + sb];
+    const int n = src_len[first + sb];
+    if (n < 13 || n >= 65536 + 11) return;                        // nothing to look up (K3 handles these sizes)
+    for (int i = lane; i < (2 << HASH_LOG) / 16; i += 32) reinterpret_cast<uint4*>(table)[i] = make_uint4(0, 0, 0, 0);
+    __syncwarp();
+    const uint32_t ph = uint32_t(reinterpret_cast<uintptr_t>(src)) & 3u;
+    const uint32_t* __restrict__ wsrc = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(src) - ph);
+    const int mflimit = n - 12;
+    const int nchunks = (mflimit + int(ph)) / 128 + 1;
+    uint2* dout = reinterpret_cast<uint2*>(g_dist + size_t(sb) * K4_DIST_STRIDE);
+    uint32_t* mout = g_mask + size_t(sb) * K4_MASK_STRIDE;
+    for (int c = 0; c < nchunks; c++) {
+        const int cp0 = 128 * c - int(ph);
+        if (lane < 2) {
+            const int pfq = cp0 + 512 + lane * 128;
+            if (pfq < n) asm volatile("prefetch.global.L2 [%0];" :: "l"(__cvta_generic_to_global(src + pfq)));
+        }
+        const int p0 = cp0 + 4 * lane;
+        uint32_t w0 = 0, w1 = 0;
+        if (p0 + 3 >= 0 && p0 <= mflimit) { w0 = wsrc[32 * c + lane]; w1 = wsrc[32 * c + lane + 1]; }
+        uint32_t seq[4], h[4]; int cand[4]; bool plaus[4];
+        seq[0] = w0; seq[1] = __funnelshift_r(w0, w1, 8); seq[2] = __funnelshift_r(w0, w1, 16); seq[3] = __funnelshift_r(w0, w1, 24);
+        #pragma unroll
+        for (int j = 0; j < 4; j++) { h[j] = (seq[j] * 2654435761u) >> (32 - HASH_LOG); cand[j] = table[h[j]]; }
+        __syncwarp();
+        #pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int p = p0 + j;
+            const bool valid = p >= 0 && p <= mflimit;
+            if (valid && (!SPARSE || j == 0)) table[h[j]] = uint16_t(p);
+            plaus[j] = valid && cand[j] < p;
+        }
+        uint32_t cseq[4];
+        #pragma unroll
+        for (int j = 0; j < 4; j++) {
+            uint32_t v = ~seq[j];
+            if (plaus[j]) { const uint32_t a = uint32_t(cand[j]) + ph; const uint32_t* w = wsrc + (a >> 2); v = __funnelshift_r(w[0], w[1], (a & 3u) * 8u); }
+            cseq[j] = v;
+        }
+        uint32_t nib = 0, dd[4];
+        #pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const bool hit = cseq[j] == seq[j];
+            dd[j] = hit ? uint32_t(p0 + j - cand[j]) : 0u;
+            nib |= uint32_t(hit) << j;
+        }
+        dout[32 * c + lane] = make_uint2(dd[0] | (dd[1] << 16), dd[2] | (dd[3] << 16));
+        uint32_t gw = nib << (4 * (lane & 7));
+        gw |= __shfl_xor_sync(B200_FULL, gw, 1); gw |= __shfl_xor_sync(B200_FULL, gw, 2); gw |= __shfl_xor_sync(B200_FULL, gw, 4);
+        if ((lane & 7) == 0) mout[4 * c + (lane >> 3)] = gw;
+        __syncwarp();                                              // this chunk's inserts precede the next chunk's lookups
+    }
+}
+
+// K2: one thread per block.  Coordinates are bytes of the aligned view (a = position + ph).
+__global__ void __launch_bounds__(128)
+lz4c4_walk_kernel(const uint8_t* __restrict__ src_base, const uint64_t* __restrict__ src_off,
+                  const int32_t* __restrict__ src_len, uint32_t first, uint32_t nsb,
+                  const uint16_t* __restrict__ g_dist, const uint32_t* __restrict__ g_mask,
+                  uint2* __restrict__ g_rec, int32_t* __restrict__ g_cnt)
+{
+    const uint32_t sb = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = lane_id();
+    const bool live = sb < nsb;
+    const uint8_t* src = live ? src_base + src_off[first + sb] : src_base;
+    const int n = live ? src_len[first + sb] : 0;
+    const bool work = live && n >= 13 && n < 65536 + 11;
+    const int ph = int(reinterpret_cast<uintptr_t>(src) & 3u);
+    const int mflimit = n - 12, matchlimit = n - 5;
+    const uint16_t* ds = g_dist + size_t(sb) * K4_DIST_STRIDE;
+    const uint32_t* mk = g_mask + size_t(sb) * K4_MASK_STRIDE;
+    uint2* rec = g_rec + size_t(sb) * K4_REC_STRIDE;
+    const int nwords = work ? ((mflimit + ph) >> 5) + 1 : 0;
+    int w = -1; uint32_t m = 0;
+    int ip = 0, anchor = 0, nrec = 0;        // positions (not view bytes)
+
+    for (;;) {
+        // ---- each lane advances to its next hit at or after ip
+        bool have = false; int ms = 0;
+        while (work) {
+            if (m == 0) {
+                w++;
+                if (w >= nwords) break;
+                m = mk[w];
+                const int lo = ip + ph - 32 * w;                   // first still-eligible bit of this word
+                if (lo >= 32) { m = 0; continue; }
+                if (lo > 0) m &= 0xFFFFFFFFu << lo;
+                continue;
+            }
+            const int q = __ffs(m) - 1;
+            m &= m - 1;
+            const int p = 32 * w + q - ph;
+            if (p < ip) continue;
+            ms = p; have = true;
+            break;
+        }
+        if (__ballot_sync(B200_FULL, have) == 0) break;            // every lane of the warp is out of hits
+        int ml = 0, dist = 0; bool longer = false;
+        if (have) {
+            dist = ds[ms + ph];
+            const int mc = ms - dist;
+            // catch-up (lz4.c:1080), at most 8 bytes
+            int back = 0;
+            const int backroom = min(min(ms - anchor, mc), 8);
+            while (back < backroom && src[ms - 1 - back] == src[mc - 1 - back]) back++;
+            // match body (lz4.c:1153): bytes are known equal for 4; compare words up to a 36-byte cap here
+            ml = 4;
+            const int lim = matchlimit - ms;
+            const int cap = min(lim, 36);
+            while (ml < cap) {
+                const uint32_t x = load_u32_unaligned(src + ms + ml) ^ load_u32_unaligned(src + mc + ml);
+                if (x) { ml += (__ffs(x) - 1) >> 3; break; }
+                ml += 4;
+            }
+            if (ml >= cap) { ml = cap; longer = cap < lim; }
+            ms -= back; ml += back;
+        }
+        // ---- matches that ran into the cap are finished by the whole warp, 128 bytes per round
+        unsigned todo = __ballot_sync(B200_FULL, longer);
+        while (todo) {
+            const int l = __ffs(todo) - 1; todo &= todo - 1;
+            const unsigned long long sp = __shfl_sync(B200_FULL, (unsigned long long)reinterpret_cast<uintptr_t>(src), l);
+            const int e_ms = __shfl_sync(B200_FULL, ms, l), e_ml = __shfl_sync(B200_FULL, ml, l);
+            const int e_dist = __shfl_sync(B200_FULL, dist, l), e_lim = __shfl_sync(B200_FULL, matchlimit, l);
+            const uint8_t* s2 = reinterpret_cast<const uint8_t*>(sp);
+            const int more = match_extend(InGlobal{s2}, e_ms + e_ml, e_ms + e_ml - e_dist, e_lim - (e_ms + e_ml), lane);
+            if (lane == l) ml += more;
+        }
+        if (have) {
+            rec[nrec++] = make_uint2(uint32_t(ms) | (uint32_t(dist) << 16), uint32_t(ml));
+            ip = anchor = ms + ml;
+            const int lo = ip + ph - 32 * w;                       // drop the hits this match covered
+            if (lo >= 32) m = 0; else if (lo > 0) m &= 0xFFFFFFFFu << lo;
+        }
+    }
+    if (live) g_cnt[sb] = nrec;
+}
+
+// K3: one warp per block writes the LZ4 stream from the records
+__global__ void __launch_bounds__(128)
+lz4c4_layout_kernel(const uint8_t* __restrict__ src_base, const uint64_t* __restrict__ src_off,
+                    const int32_t* __restrict__ src_len,
+                    uint8_t* __restrict__ dst_base, const uint64_t* __restrict__ dst_off,
+                    const int32_t* __restrict__ dst_cap, int32_t* __restrict__ result, uint32_t first, uint32_t nsb,
+                    const uint2* __restrict__ g_rec, const int32_t* __restrict__ g_cnt)
+{
+    const uint32_t sb = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (sb >= nsb) return;
+    const uint32_t b = first + sb;
+    const int lane = lane_id();
+    const uint8_t* __restrict__ src = src_base + src_off[b];
+    uint8_t* __restrict__ dst = dst_base + dst_off[b];
+    const int n = src_len[b];
+    const int cap = dst_cap[b];
+    int ret = 0;
+    if (n < 0 || n >= 65536 + 11) goto done;
+    if (n == 0) { if (cap >= 1) { if (lane == 0) dst[0] = 0; ret = 1; } goto done; }
+    {
+        const int cnt = n >= 13 ? g_cnt[sb] : 0;
+        const uint2* rec = g_rec + size_t(sb) * K4_REC_STRIDE;
+        int op = 0, anchor = 0;
+        for (int base = 0; base < cnt; base += 32) {
+            const int k = base + lane;
+            const bool on = k < cnt;
+            uint2 r = make_uint2(0, 4);
+            if (on) r = rec[k];
+            const int ms = int(r.x & 0xFFFFu), dist = int(r.x >> 16), ml = int(r.y);
+            const int end = ms + ml;
+            int prev_end = __shfl_up_sync(B200_FULL, end, 1);
+            if (lane == 0) prev_end = anchor;
+            const int lit = on ? ms - prev_end : 0, mcode = ml - 4;
+            const int lhdr = lit >= 15 ? (lit - 15) / 255 + 1 : 0;
+            const int mhdr = mcode >= 15 ? (mcode - 15) / 255 + 1 : 0;
+            const int size = on ? 1 + lhdr + lit + 2 + mhdr : 0;
+            int incl = size;
+            #pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(B200_FULL, incl, d); if (lane >= d) incl += y; }
+            const int total = __shfl_sync(B200_FULL, incl, 31);
+            if (uint32_t(op) + uint32_t(total) > uint32_t(cap)) goto done;                        // lz4.c:1085-1088, 1158
+            const int o = op + incl - size;
+            if (on) {
+                uint8_t* d = dst + o;
+                d[0] = uint8_t((min(lit, 15) << 4) | min(mcode, 15));
+                d += 1;
+                if (lit >= 15) { int v = lit - 15; for (; v >= 255; v -= 255) *d++ = 255; *d++ = uint8_t(v); }
+                d += lit;
+                d[0] = uint8_t(dist); d[1] = uint8_t(dist >> 8);
+                d += 2;
+                if (mcode >= 15) { int v = mcode - 15; for (; v >= 255; v -= 255) *d++ = 255; *d++ = uint8_t(v); }
+            }
+            const int nk = min(32, cnt - base);
+            for (int kk = 0; kk < nk; kk++) {
+                const int ka = __shfl_sync(B200_FULL, prev_end, kk);
+                const int kl = __shfl_sync(B200_FULL, lit, kk);
+                const int ko = __shfl_sync(B200_FULL, o + 1 + lhdr, kk);
+                warp_copy(dst + ko, src + ka, kl, lane);
+            }
+            op += total;
+            anchor = __shfl_sync(B200_FULL, end, nk - 1);
+        }
+        {   // last literals (lz4.c:1266-1293)
+            const int lit = n - anchor;
+            const int lhdr = lit >= 15 ? (lit - 15) / 255 + 1 : 0;
+            if (uint32_t(op) + 1u + uint32_t(lhdr) + uint32_t(lit) > uint32_t(cap)) goto done;
+            if (lane == 0) dst[op] = uint8_t(min(lit, 15) << 4);
+            op += 1;
+            if (lhdr) { write_len_ext(dst + op, lit - 15, lhdr, lane); op += lhdr; }
+            warp_copy(dst + op, src + anchor, lit, lane);
+            ret = op + lit;
+        }
+    }
+done:
+    if (lane == 0) result[b] = ret;
+}
+
+// scratch arena: one per (calling thread, stream) so concurrent pipelines never share it
+struct K4Arena { cudaStream_t st; int device; uint32_t blocks; uint16_t* dist; uint32_t* mask; uint2* rec; int32_t* cnt; };
+static thread_local K4Arena t_arenas[8];
+static thread_local int t_narenas = 0;
+extern "C" { int b200lz4_compress_subbatch = 16384; }   // blocks per K1/K2/K3 round (arena = 270 KB per block)
+
+static cudaError_t k4_arena(cudaStream_t st, uint32_t blocks, K4Arena** out)
+{
+    int dev = 0; cudaError_t e = cudaGetDevice(&dev); if (e != cudaSuccess) return e;
+    K4Arena* a = nullptr;
+    for (int i = 0; i < t_narenas; i++) if (t_arenas[i].st == st && t_arenas[i].device == dev) a = &t_arenas[i];
+    if (!a) {
+        if (t_narenas == 8) { a = &t_arenas[0]; cudaFree(a->dist); cudaFree(a->mask); cudaFree(a->rec); cudaFree(a->cnt); }
+        else a = &t_arenas[t_narenas++];
+        *a = K4Arena{st, dev, 0, nullptr, nullptr, nullptr, nullptr};
+    }
+    if (a->blocks < blocks) {
+        if (a->dist) { cudaFree(a->dist); cudaFree(a->mask); cudaFree(a->rec); cudaFree(a->cnt); }
+        a->blocks = 0;
+        if ((e = cudaMalloc(&a->dist, size_t(blocks) * K4_DIST_STRIDE * 2)) != cudaSuccess) return e;
+        if ((e = cudaMalloc(&a->mask, size_t(blocks) * K4_MASK_STRIDE * 4)) != cudaSuccess) return e;
+        if ((e = cudaMalloc(&a->rec, size_t(blocks) * K4_REC_STRIDE * 8)) != cudaSuccess) return e;
+        if ((e = cudaMalloc(&a->cnt, size_t(blocks) * 4)) != cudaSuccess) return e;
+        a->blocks = blocks;
+    }
+    *out = a;
+    return cudaSuccess;
+}
+
+template <int HASH_LOG, bool SPARSE>
+static cudaError_t launch_v4(const BatchArgs& a, cudaStream_t st)
+{
+    const uint32_t sbmax = (uint32_t)std::min<size_t>(a.n, (size_t)std::max(b200lz4_compress_subbatch, 32));
+    K4Arena* ar; cudaError_t e = k4_arena(st, sbmax, &ar); if (e != cudaSuccess) return e;
+    auto k1 = lz4c4_lookup_kernel<HASH_LOG, SPARSE>;
+    const size_t smem = 2u << HASH_LOG;
+    if ((e = cudaFuncSetAttribute(k1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+    cudaFuncSetAttribute(k1, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    for (size_t first = 0; first < a.n; first += sbmax) {
+        const uint32_t nsb = (uint32_t)std::min<size_t>(sbmax, a.n - first);
+        k1<<<nsb, 32, smem, st>>>(a.src_base, a.src_off, a.src_len, (uint32_t)first, nsb, ar->dist, ar->mask);
+        lz4c4_walk_kernel<<<(nsb + 127) / 128, 128, 0, st>>>(a.src_base, a.src_off, a.src_len, (uint32_t)first, nsb, ar->dist, ar->mask, ar->rec, ar->cnt);
+        lz4c4_layout_kernel<<<(nsb + 3) / 4, 128, 0, st>>>(a.src_base, a.src_off, a.src_len, a.dst_base, a.dst_off, a.dst_cap, a.result,
+                                                          (uint32_t)first, nsb, ar->rec, ar->cnt);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
 template <int HASH_LOG, bool U16, bool STAGE>
 static cudaError_t launch_variant(const BatchArgs& a, cudaStream_t st)
 {
@@ -625,7 +918,11 @@ cudaError_t launch_compress_fast(const BatchArgs& a, int max_src_len, cudaStream
 {
     if (a.n == 0) return cudaSuccess;
     const bool u16 = max_src_len > 0 && max_src_len <= 65536;
-    if (b200lz4_compress_algo == 3 && !b200lz4_compress_stage) {
+    if (b200lz4_compress_algo == 4 && !b200lz4_compress_stage && u16) {
+        if (b200lz4_compress_hash_log == 12) return b200lz4_compress_sparse ? launch_v4<12, true>(a, st) : launch_v4<12, false>(a, st);
+        return b200lz4_compress_sparse ? launch_v4<13, true>(a, st) : launch_v4<13, false>(a, st);
+    }
+    if ((b200lz4_compress_algo == 3 || b200lz4_compress_algo == 4) && !b200lz4_compress_stage) {
         if (!u16) return launch_v3<12, false, false>(a, st);
         if (b200lz4_compress_hash_log == 12) return b200lz4_compress_sparse ? launch_v3<12, true, true>(a, st) : launch_v3<12, true, false>(a, st);
         return b200lz4_compress_sparse ? launch_v3<13, true, true>(a, st) : launch_v3<13, true, false>(a, st);

@@ -114,13 +114,13 @@ def _knob(b200, name, value):
     ctypes.c_int.in_dll(b200._native.lib(), name).value = value
 
 
-@pytest.mark.parametrize("table", ["u16", "u16_hl12", "u16_sparse", "u16_hl12_sparse", "u32", "v2_u16", "v2_u32", "v1_u16", "v1_u16_hl12", "v1_u16_tma_staged", "v1_u32"])
+@pytest.mark.parametrize("table", ["u16", "u16_hl12", "u16_sparse", "u16_hl12_sparse", "u32", "v4_u16", "v4_u16_hl12_sparse", "v4_u32", "v2_u16", "v2_u32", "v1_u16", "v1_u16_hl12", "v1_u16_tma_staged", "v1_u32"])
 def test_compress_roundtrip_through_oracle(b200, checker, table):
     items = corpus.blocks(checker) + corpus.calgary_blocks()
     if not table.endswith("u32"):           # 16-bit position table: caller promises blocks <= 64 KiB
         items = [(nm, d) for nm, d in items if len(d) <= 65536]
     max_src_len = 0 if table.endswith("u32") else 65536
-    _knob(b200, "b200lz4_compress_algo", 1 if table.startswith("v1") else 2 if table.startswith("v2") else 3)   # 3 = two-warp pipeline (default)
+    _knob(b200, "b200lz4_compress_algo", 1 if table.startswith("v1") else 2 if table.startswith("v2") else 4 if table.startswith("v4") else 3)   # 3 = two-warp pipeline (default)
     _knob(b200, "b200lz4_compress_hash_log", 12 if "hl12" in table else 13)
     _knob(b200, "b200lz4_compress_stage", 1 if "staged" in table else 0)
     _knob(b200, "b200lz4_compress_sparse", 1 if "sparse" in table else 0)
