@@ -340,7 +340,7 @@ def run_b200(args):
             "compress_gibs": total_bytes / (t_comp_ms / 1e3) / GIB,
             "decompress_gibs": total_bytes / (t_dec_ms / 1e3) / GIB,
             "ratio": total_bytes / total_comp,
-            "roofline": {"bound": "hbm", "kernel": "lz4_compress_fast2_kernel<13,u16>" if args.hash_log == 13 else "lz4_compress_fast2_kernel<12,u16>", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": f"lz4_compress_fast3_kernel<{args.hash_log},u16>", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "frac_of_nominal_8TBs": achieved / 8000.0,
                          "traffic": traffic, "algorithmic_bytes_per_launch": algo_bytes, "peak_source": peak_src,
                          "decompress_achieved": algo_bytes / (t_dec_ms / 1e3) / 1e9},
