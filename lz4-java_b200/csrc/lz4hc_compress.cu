@@ -23,9 +23,8 @@
 namespace b200 {
 
 // bucket count is a template parameter: 2048 buckets (128 KiB, 1 CTA/SM) or 1024 buckets (64 KiB, 3 CTAs/SM)
-static constexpr int HC_WAYS = 32;
 static constexpr int HC_LANE_CAP = 64;                 // per-lane extension cap; the winner is extended cooperatively
-template <int BL> constexpr size_t hc_smem() { return (size_t(2) << BL) * HC_WAYS + (size_t(4) << BL); }
+template <int BL, int WAYS> constexpr size_t hc_smem() { return (size_t(2) << BL) * WAYS + (size_t(4) << BL); }
 
 struct HcTable {
     uint16_t* ring;      // [bucket][way]
@@ -34,46 +33,49 @@ struct HcTable {
 
 template <int BL> __device__ __forceinline__ uint32_t hc_hash(uint32_t seq) { return (seq * 2654435761u) >> (32 - BL); }
 
-// insert positions [lo, hi) — every position, like LZ4HC_Insert
-template <int BL, class In>
-__device__ __forceinline__ void hc_insert(const In& in, const HcTable& t, int lo, int hi, int lane)
+// Longest match for position p among its bucket's WAYS most recent occurrences.  WAYS = 32: one position per
+// warp; WAYS = 16: each half-warp searches its own position (p differs between the halves).  Returns ml
+// (0 if < 4) and the distance, uniform within the searching group of lanes.
+template <int BL, int WAYS, class In>
+__device__ __forceinline__ int hc_search(const In& in, const HcTable& t, int p, bool valid, int matchlimit, int lane, int& dist_out)
 {
-    for (int p = lo + lane; p < hi; p += 32) {
-        const uint32_t h = hc_hash<BL>(in.ld4(p));
-        const uint32_t slot = atomicAdd(&t.head[h], 1u) & (HC_WAYS - 1);
-        t.ring[h * HC_WAYS + slot] = uint16_t(p);
-    }
-    __syncwarp();
-}
-
-// longest match for position p among the bucket's 32 most recent occurrences: returns ml (0 if < 4) and distance
-template <int BL, class In>
-__device__ __forceinline__ int hc_search(const In& in, const HcTable& t, int p, int matchlimit, int lane, int& dist_out)
-{
-    const uint32_t seq = in.ld4(p);
-    const uint32_t h = hc_hash<BL>(seq);
-    const uint32_t cnt = t.head[h];
-    const uint32_t c16 = t.ring[h * HC_WAYS + lane];
-    const int dist = int((uint32_t(p) - c16) & 0xFFFFu);          // window-relative: any alias is re-verified on the bytes
-    const int cand = p - dist;
-    int ml = 0;
-    if (lane < (int)min(cnt, (uint32_t)HC_WAYS) && dist != 0 && cand >= 0 && in.ld4(cand) == seq) {
-        const int maxlen = min(matchlimit - p, HC_LANE_CAP);
-        ml = 4;
-        while (ml < maxlen) {
-            const uint32_t x = in.ld4(p + ml) ^ in.ld4(cand + ml);
-            if (x) { ml += (__ffs(x) - 1) >> 3; break; }
-            ml += 4;
+    const int l = lane & (WAYS - 1);
+    int ml = 0, dist = 0;
+    if (valid) {
+        const uint32_t seq = in.ld4(p);
+        const uint32_t h = hc_hash<BL>(seq);
+        const uint32_t cnt = t.head[h];
+        const uint32_t c16 = t.ring[h * WAYS + l];
+        dist = int((uint32_t(p) - c16) & 0xFFFFu);                 // window-relative: any alias is re-verified on the bytes
+        const int cand = p - dist;
+        if (l < (int)min(cnt, (uint32_t)WAYS) && dist != 0 && cand >= 0 && in.ld4(cand) == seq) {
+            const int maxlen = min(matchlimit - p, HC_LANE_CAP);
+            ml = 4;
+            while (ml < maxlen) {
+                const uint32_t x = in.ld4(p + ml) ^ in.ld4(cand + ml);
+                if (x) { ml += (__ffs(x) - 1) >> 3; break; }
+                ml += 4;
+            }
+            ml = min(ml, maxlen);
         }
-        ml = min(ml, maxlen);
     }
-    // longest wins, nearest among equals: pack (ml, 65535 - dist)
-    const uint32_t key = (uint32_t(ml) << 16) | uint32_t(65535 - dist);
-    const uint32_t best = __reduce_max_sync(B200_FULL, ml >= 4 ? key : 0u);
-    int bml = int(best >> 16);
-    dist_out = 65535 - int(best & 0xFFFFu);
-    if (bml >= HC_LANE_CAP && p + bml < matchlimit)               // capped: finish the count with all lanes
-        bml += match_extend(in, p + bml, p - dist_out + bml, matchlimit - (p + bml), lane);
+    // longest wins, nearest among equals: pack (ml, 65535 - dist); butterfly max inside the group of WAYS lanes
+    uint32_t key = ml >= 4 ? ((uint32_t(ml) << 16) | uint32_t(65535 - dist)) : 0u;
+    #pragma unroll
+    for (int d = 1; d < WAYS; d <<= 1) key = max(key, __shfl_xor_sync(B200_FULL, key, d));
+    int bml = int(key >> 16);
+    dist_out = 65535 - int(key & 0xFFFFu);
+    // capped candidates: finish the count with all 32 lanes, one group after the other
+    #pragma unroll
+    for (int g = 0; g < 32 / WAYS; g++) {
+        const int src_lane = g * WAYS;
+        const int gp = __shfl_sync(B200_FULL, p, src_lane), gml = __shfl_sync(B200_FULL, bml, src_lane);
+        const int gd = __shfl_sync(B200_FULL, dist_out, src_lane);
+        if (gml >= HC_LANE_CAP && gp + gml < matchlimit) {
+            const int more = match_extend(in, gp + gml, gp - gd + gml, matchlimit - (gp + gml), lane);
+            if (lane / WAYS == g) bml += more;
+        }
+    }
     return bml;
 }
 
@@ -82,7 +84,7 @@ __device__ __forceinline__ int hc_search(const In& in, const HcTable& t, int p, 
 // wide), then every thread takes the same decision from the four results: first position with a match,
 // then move right while the next position's match is strictly longer (the idea of lz4hc.c:599-732,
 // simplified).  Stretches without matches advance four positions per round.
-template <int BL>
+template <int BL, int WAYS>
 __global__ void __launch_bounds__(128)
 lz4hc_compress_kernel(const uint8_t* __restrict__ src_base, const uint64_t* __restrict__ src_off,
                       const int32_t* __restrict__ src_len,
@@ -92,8 +94,9 @@ lz4hc_compress_kernel(const uint8_t* __restrict__ src_base, const uint64_t* __re
     extern __shared__ __align__(16) uint8_t smem_raw[];
     HcTable t;
     t.ring = reinterpret_cast<uint16_t*>(smem_raw);
-    t.head = reinterpret_cast<uint32_t*>(smem_raw + (size_t(2) << BL) * HC_WAYS);
-    int* s_res = reinterpret_cast<int*>(smem_raw + hc_smem<BL>());              // [4][2] (ml, dist), [8] = fail flag
+    t.head = reinterpret_cast<uint32_t*>(smem_raw + (size_t(2) << BL) * WAYS);
+    constexpr int PER_WARP = 32 / WAYS, ROUND = 4 * PER_WARP;                   // positions searched per round
+    int* s_res = reinterpret_cast<int*>(smem_raw + hc_smem<BL, WAYS>());        // [ROUND][2] (ml, dist), [16] = fail flag
 
     const uint32_t b = blockIdx.x;
     if (b >= nblocks) return;
@@ -107,7 +110,7 @@ lz4hc_compress_kernel(const uint8_t* __restrict__ src_base, const uint64_t* __re
     if (n == 0) { if (tid == 0) { if (cap >= 1) dst[0] = 0; result[b] = cap >= 1 ? 1 : 0; } return; }
 
     for (int i = tid; i < (1 << BL); i += 128) t.head[i] = 0;
-    if (tid == 0) s_res[8] = 0;
+    if (tid == 0) s_res[16] = 0;
     const InGlobal in{src};
     const int mflimit = n - 12, matchlimit = n - 5;                                              // lz4hc.c:566-567
     const int max_lazy = level >= 9 ? 3 : (level >= 4 ? 1 : 0);
@@ -117,29 +120,30 @@ lz4hc_compress_kernel(const uint8_t* __restrict__ src_base, const uint64_t* __re
 
     while (ip <= mflimit) {
         // every position below ip+4 goes into its bucket ring (LZ4HC_Insert, lz4hc.c:120-141), 128 per pass
-        const int ins_end = min(ip + 4, mflimit + 1);
+        const int ins_end = min(ip + ROUND, mflimit + 1);
         for (int p = inserted + tid; p < ins_end; p += 128) {
             const uint32_t h = hc_hash<BL>(in.ld4(p));
-            const uint32_t slot = atomicAdd(&t.head[h], 1u) & (HC_WAYS - 1);
-            t.ring[h * HC_WAYS + slot] = uint16_t(p);
+            const uint32_t slot = atomicAdd(&t.head[h], 1u) & (WAYS - 1);
+            t.ring[h * WAYS + slot] = uint16_t(p);
         }
         inserted = max(inserted, ins_end);
         __syncthreads();
         {
-            const int p = ip + warp;
-            int dist = 0, ml = 0;
-            if (p <= mflimit) ml = hc_search<BL>(in, t, p, matchlimit, lane, dist);
-            if (lane == 0) { s_res[2 * warp] = ml; s_res[2 * warp + 1] = dist; }
+            const int slot = warp * PER_WARP + lane / WAYS;
+            const int p = ip + slot;
+            int dist = 0;
+            const int ml = hc_search<BL, WAYS>(in, t, p, p <= mflimit, matchlimit, lane, dist);
+            if ((lane & (WAYS - 1)) == 0) { s_res[2 * slot] = ml; s_res[2 * slot + 1] = dist; }
         }
         __syncthreads();
         int cur = -1;
         #pragma unroll
-        for (int k = 3; k >= 0; k--) if (s_res[2 * k] >= 4) cur = k;
-        const bool failed = s_res[8] != 0;
+        for (int k = ROUND - 1; k >= 0; k--) if (s_res[2 * k] >= 4) cur = k;
+        const bool failed = s_res[16] != 0;
         __syncthreads();                                            // results consumed before the next round overwrites them
         if (failed) break;
-        if (cur < 0) { ip += 4; continue; }
-        for (int k = 0; k < max_lazy && cur < 3; k++) {
+        if (cur < 0) { ip += ROUND; continue; }
+        for (int k = 0; k < max_lazy && cur < ROUND - 1; k++) {
             if (s_res[2 * (cur + 1)] > s_res[2 * cur]) cur++; else break;
         }
         int ms = ip + cur, ml = s_res[2 * cur];
@@ -153,14 +157,14 @@ lz4hc_compress_kernel(const uint8_t* __restrict__ src_base, const uint64_t* __re
             Seq q{anchor, ms - back, dist, ml + back};
             uint32_t litv = 0;
             if (lane < q.ms - anchor && q.ms - anchor <= 32) litv = in.ld1(anchor + lane);
-            if (!emit_sequence(in, q, litv, dst, op, cap, lane)) { if (lane == 0) s_res[8] = 1; }
+            if (!emit_sequence(in, q, litv, dst, op, cap, lane)) { if (lane == 0) s_res[16] = 1; }
         }
         ip = anchor = ms + ml;
     }
     __syncthreads();
     if (warp == 0) {
         int ret = 0;
-        if (s_res[8] == 0) {
+        if (s_res[16] == 0) {
             const int lit = n - anchor;                                       // last literals (lz4hc.c:737-770)
             const int lhdr = lit >= 15 ? (lit - 15) / 255 + 1 : 0;
             if ((long long)op + 1 + lhdr + lit <= cap) {
@@ -175,16 +179,21 @@ lz4hc_compress_kernel(const uint8_t* __restrict__ src_base, const uint64_t* __re
     }
 }
 
-extern "C" { int b200lz4_hc_bucket_log = 11; }   // tuning knob: 11 = 2048 buckets (128 KiB), 10 = 1024 buckets (64 KiB, 3 CTAs/SM)
+extern "C" {
+int b200lz4_hc_bucket_log = 11;   // 11 = 2048 buckets, 10 = 1024 buckets
+int b200lz4_hc_ways = 32;         // 32 = one position per warp (128 KiB table at 2048 buckets, 1 CTA/SM, best ratio);
+                                  // 16 = one position per half-warp, 8 positions per round (64 KiB, 3 CTAs/SM)
+}
 
-template <int BL>
+template <int BL, int WAYS>
 static cudaError_t launch_hc(const BatchArgs& a, int level, cudaStream_t st)
 {
-    auto k = lz4hc_compress_kernel<BL>;
-    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hc_smem<BL>() + 64);
+    auto k = lz4hc_compress_kernel<BL, WAYS>;
+    const size_t smem = hc_smem<BL, WAYS>() + 80;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    k<<<(unsigned)a.n, 128, hc_smem<BL>() + 64, st>>>(a.src_base, a.src_off, a.src_len, a.dst_base, a.dst_off,
-                                              a.dst_cap, a.result, (uint32_t)a.n, level);
+    k<<<(unsigned)a.n, 128, smem, st>>>(a.src_base, a.src_off, a.src_len, a.dst_base, a.dst_off,
+                                        a.dst_cap, a.result, (uint32_t)a.n, level);
     return cudaGetLastError();
 }
 
@@ -192,7 +201,8 @@ cudaError_t launch_compress_hc(const BatchArgs& a, int level, cudaStream_t st)
 {
     if (a.n == 0) return cudaSuccess;
     if (level < 1) level = 9;                                                 // LZ4HC_CLEVEL_DEFAULT, lz4hc.c:840
-    return b200lz4_hc_bucket_log == 10 ? launch_hc<10>(a, level, st) : launch_hc<11>(a, level, st);
+    if (b200lz4_hc_ways == 16) return b200lz4_hc_bucket_log == 10 ? launch_hc<10, 16>(a, level, st) : launch_hc<11, 16>(a, level, st);
+    return b200lz4_hc_bucket_log == 10 ? launch_hc<10, 32>(a, level, st) : launch_hc<11, 32>(a, level, st);
 }
 
 } // namespace b200

@@ -112,12 +112,18 @@ def config4(chk, out):
     comp = torch.zeros(nblk * stride, device=dev, dtype=torch.uint8)
     clen = torch.zeros(nblk, device=dev, dtype=torch.int32)
     res = {}
-    for bl in (11, 10):
+    for bl, ways in ((11, 32), (11, 16), (10, 32), (10, 16)):
         C.c_int.in_dll(L._native.lib(), "b200lz4_hc_bucket_log").value = bl
+        C.c_int.in_dll(L._native.lib(), "b200lz4_hc_ways").value = ways
         t = timeit(lambda: L.batch.compress_hc_batch_dev(src, soff, slen, comp, coff, ccap, clen, 9), iters=2, warm=1)
         csum = int(clen.sum().item())
-        res[f"buckets_{1 << bl}"] = {"GiBps": nblk * bs / t / GIB, "ratio": nblk * bs / csum}
+        out_ = torch.zeros(nblk * bs, device=dev, dtype=torch.uint8); r_ = torch.zeros(nblk, device=dev, dtype=torch.int32)
+        L.batch.decompress_safe_batch_dev(comp, coff, clen, out_, soff, slen, r_)
+        assert bool((r_ == bs).all().item()) and bool(torch.equal(out_, src)), "HC round trip"
+        del out_
+        res[f"buckets_{1 << bl}_ways_{ways}"] = {"GiBps": nblk * bs / t / GIB, "ratio": nblk * bs / csum}
     C.c_int.in_dll(L._native.lib(), "b200lz4_hc_bucket_log").value = 11
+    C.c_int.in_dll(L._native.lib(), "b200lz4_hc_ways").value = 32
     ref_c = sum(len(chk.compress_hc(host[i * bs:(i + 1) * bs], 9)) for i in range(8)) if hasattr(chk, "compress_hc") else None
     t0 = time.perf_counter()
     if hasattr(chk, "compress_hc"):
