@@ -381,198 +381,190 @@ static cudaError_t launch_v2(const BatchArgs& a, cudaStream_t st)
 }
 
 // ---------------------------------------------------------------------------------------------
-// Two-warp pipeline (algo 3): the decoupled parser above, split across a producer/consumer pair so the
-// serial walk carries nothing but the walk.
+// Warp-specialised pipeline (algo 3): the decoupled parser above, split across producer/consumer warps of
+// one CTA so the serial walk carries nothing but the walk.
 //
-//   warp L ("lookup + layout"): phase AB for chunk s, then writes out the sequences the parser found
-//                               in chunk s-2 (sizes, prefix sum of output offsets, 32 tokens/offsets by
-//                               32 lanes, cooperative literal copies) — all throughput work.
-//   warp P ("parser"):          greedy walk of chunk s-1: next hit, its distance, one cooperative
-//                               compare round, and a 16-byte record in shared memory.  ~65 instructions
-//                               and one L2 round trip per sequence instead of ~130 + the copies.
-// One CTA barrier per 128-position chunk hands the double-buffered chunk state (distances, hit mask,
-// records) over.  Same parse, same output bytes as algo 2.
-struct SeqRec { int anchor, ms, dist, ml; };
+//   warp L ("lookup"):  phase AB for chunk c — hash, table probe + insert, candidate verification — and
+//                       publishes the chunk's distances (u16 per position) and hit masks in shared memory.
+//   warp P ("parser"):  greedy walk of chunk c.  Every lane takes one of the chunk's next 32 hits and measures
+//                       it on its own (catch-up of up to 4 bytes, body up to 32 bytes), so 32 extension loads
+//                       are in flight at once; each lane then finds its successor (first hit starting at or
+//                       after its own end) by a shuffle binary search over the sorted hit positions, and the
+//                       greedy chain is one shuffle per selected sequence.  Selected lanes write 8-byte records.
+//   warp E ("emit"):    sizes, prefix sum of output offsets, 32 tokens/offsets by 32 lanes, lane-parallel
+//                       literal copies, last literals, result.  With B200_V3_WARPS == 2 warp L does this
+//                       after its lookup phase (one chunk behind the parser).
+// Chunk state is double-buffered; the hand-offs are named barriers (producer bar.arrive, consumer bar.sync),
+// so no warp waits for a warp it does not depend on.  Same parse, same output bytes as algo 2.
+#ifndef B200_V3_NB
+#define B200_V3_NB 2
+#endif
+#ifndef B200_V3_WARPS
+#define B200_V3_WARPS 2
+#endif
+#ifndef B200_V3_MINB
+#define B200_V3_MINB 12
+#endif
+#ifndef B200_V3_MINB12
+#define B200_V3_MINB12 16
+#endif
+// (Immediate barrier ids, so ptxas reserves only the barriers in use and not all 16.)
+#define B200_BAR_CASE(OP, N) case N: asm volatile(OP " " #N ", 64;" ::: "memory"); break;
+__device__ __forceinline__ void bar_arrive(int id)
+{
+    switch (id) { B200_BAR_CASE("bar.arrive", 1) B200_BAR_CASE("bar.arrive", 2) B200_BAR_CASE("bar.arrive", 3)
+                  B200_BAR_CASE("bar.arrive", 4) B200_BAR_CASE("bar.arrive", 5) B200_BAR_CASE("bar.arrive", 6)
+                  B200_BAR_CASE("bar.arrive", 7) default: asm volatile("bar.arrive 8, 64;" ::: "memory"); }
+}
+__device__ __forceinline__ void bar_wait(int id)
+{
+    switch (id) { B200_BAR_CASE("bar.sync", 1) B200_BAR_CASE("bar.sync", 2) B200_BAR_CASE("bar.sync", 3)
+                  B200_BAR_CASE("bar.sync", 4) B200_BAR_CASE("bar.sync", 5) B200_BAR_CASE("bar.sync", 6)
+                  B200_BAR_CASE("bar.sync", 7) default: asm volatile("bar.sync 8, 64;" ::: "memory"); }
+}
 
-template <int HASH_LOG, bool U16, bool SPARSE>
-__global__ void __launch_bounds__(64)
+template <int HASH_LOG, bool SPARSE>
+__global__ void __launch_bounds__(32 * B200_V3_WARPS, HASH_LOG == 13 ? B200_V3_MINB : B200_V3_MINB12)
 lz4_compress_fast3_kernel(const uint8_t* __restrict__ src_base, const uint64_t* __restrict__ src_off,
                           const int32_t* __restrict__ src_len,
                           uint8_t* __restrict__ dst_base, const uint64_t* __restrict__ dst_off,
                           const int32_t* __restrict__ dst_cap, int32_t* __restrict__ result, uint32_t nblocks)
 {
-    using Entry = typename std::conditional<U16, uint16_t, uint32_t>::type;
-    constexpr int TABLE_BYTES = int(sizeof(Entry) << HASH_LOG);
+    constexpr int NB = B200_V3_NB, NW = B200_V3_WARPS;
+    constexpr int LAG = NB - 1;                            // NW == 2: warp L emits chunk i-LAG after looking chunk i up
+    constexpr int BAR_FULL = 1, BAR_WALKED = 1 + NB, BAR_DFREE = 1 + 2 * NB, BAR_RFREE = 1 + 3 * NB;
+    static_assert(NW == 2 || 4 * NB <= 8, "named barrier ids 1..8");
+    constexpr int TABLE_BYTES = 2 << HASH_LOG;
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    Entry* table = reinterpret_cast<Entry*>(smem_raw);
-    uint16_t* s_dist = reinterpret_cast<uint16_t*>(smem_raw + TABLE_BYTES);                 // [2][128]
-    SeqRec* s_rec = reinterpret_cast<SeqRec*>(smem_raw + TABLE_BYTES + 512);                // [2][32]
-    uint32_t* s_mask = reinterpret_cast<uint32_t*>(smem_raw + TABLE_BYTES + 512 + 1024);    // [2][4]
-    int* s_cnt = reinterpret_cast<int*>(s_mask + 8);                                        // [2] records per buffer, [2] = final anchor
+    uint16_t* table = reinterpret_cast<uint16_t*>(smem_raw);
+    uint16_t* s_dist = reinterpret_cast<uint16_t*>(smem_raw + TABLE_BYTES);                 // [NB][128] distance per position, 0 = no match
+    uint2* s_rec = reinterpret_cast<uint2*>(smem_raw + TABLE_BYTES + NB * 256);             // [NB][32]  x = start | distance << 16, y = length
+    uint32_t* s_mask = reinterpret_cast<uint32_t*>(smem_raw + TABLE_BYTES + NB * 256 + NB * 256);   // [NB][4] hit masks
+    int* s_cnt = reinterpret_cast<int*>(s_mask + 4 * NB);                                   // [NB] records per buffer
+    uint8_t* s_hit = reinterpret_cast<uint8_t*>(s_cnt + 4);                                 // [128] ranked hit positions (warp P's scratch)
 
     const uint32_t b = blockIdx.x;
     if (b >= nblocks) return;
     const int lane = lane_id();
-    const bool isL = (threadIdx.x >> 5) == 0;
+    const int role = threadIdx.x >> 5;                     // 0 = L, 1 = P, 2 = E
     const uint8_t* __restrict__ src = src_base + src_off[b];
     uint8_t* __restrict__ dst = dst_base + dst_off[b];
     const int n = src_len[b];
     const int cap = dst_cap[b];
 
-    if (n < 0 || n > 0x7E000000 || (U16 && n >= 65536 + 11)) { if (threadIdx.x == 0) result[b] = 0; return; }   // lz4.c:1324, 973
+    if (n < 0 || n >= 65536 + 11) { if (threadIdx.x == 0) result[b] = 0; return; }               // lz4.c:1324, 973
     if (n == 0) { if (threadIdx.x == 0) { if (cap >= 1) dst[0] = 0; result[b] = cap >= 1 ? 1 : 0; } return; }
 
     const uint32_t ph = uint32_t(reinterpret_cast<uintptr_t>(src)) & 3u;
     const uint32_t* __restrict__ wsrc = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(src) - ph);
     const int mflimit = n - 12, matchlimit = n - 5;
     const int nchunks = (mflimit + int(ph)) / 128 + 1;
-
-    if (isL) {
-        for (int i = lane; i < TABLE_BYTES / 16; i += 32) reinterpret_cast<uint4*>(table)[i] = make_uint4(0, 0, 0, 0);
-        if (lane < 3) s_cnt[lane] = 0;
-        __syncwarp();
-    }
     auto ld4 = [&](int pos) -> uint32_t {
         const uint32_t a = uint32_t(pos) + ph;
         const uint32_t* w = wsrc + (a >> 2);
         return __funnelshift_r(w[0], w[1], (a & 3u) * 8u);
     };
 
-    int op = 0; bool fail = false;          // warp L
-    int ip = 0, anchor = 0;                 // warp P
-    asm volatile("bar.sync 1, 64;" ::: "memory");
+    // ------------------------------------------------------------------ phase AB for chunk c (warp L)
+    auto lookup = [&](int c) {
+        const int cp0 = 128 * c - int(ph), buf = c % NB;
+        if (lane < 2) {
+            const int pfq = cp0 + 512 + lane * 128;
+            if (pfq < n) asm volatile("prefetch.global.L2 [%0];" :: "l"(__cvta_generic_to_global(src + pfq)));
+        }
+        const int p0 = cp0 + 4 * lane;
+        uint32_t w0 = 0, w1 = 0;
+        if (p0 + 3 >= 0 && p0 <= mflimit) { w0 = wsrc[32 * c + lane]; w1 = wsrc[32 * c + lane + 1]; }
+        uint32_t seq[4], h[4]; int cand[4]; bool plaus[4];
+        seq[0] = w0; seq[1] = __funnelshift_r(w0, w1, 8); seq[2] = __funnelshift_r(w0, w1, 16); seq[3] = __funnelshift_r(w0, w1, 24);
+        #pragma unroll
+        for (int j = 0; j < 4; j++) { h[j] = (seq[j] * 2654435761u) >> (32 - HASH_LOG); cand[j] = table[h[j]]; }
+        __syncwarp();  // every lookup of the chunk precedes every insert (same-slot stores: any winner is a valid position)
+        #pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int p = p0 + j;
+            const bool valid = p >= 0 && p <= mflimit;
+            // SPARSE: only one position in four is published (every position is still probed)
+            if (valid && (!SPARSE || j == 0)) table[h[j]] = uint16_t(p);
+            plaus[j] = valid && cand[j] < p;
+        }
+        uint32_t cseq[4];
+        #pragma unroll
+        for (int j = 0; j < 4; j++) cseq[j] = plaus[j] ? ld4(cand[j]) : ~seq[j];
+        uint32_t nib = 0, dd[4];
+        #pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const bool hit = cseq[j] == seq[j];
+            dd[j] = hit ? uint32_t(p0 + j - cand[j]) : 0u;
+            nib |= uint32_t(hit) << j;
+        }
+        reinterpret_cast<uint2*>(s_dist + 128 * buf)[lane] = make_uint2(dd[0] | (dd[1] << 16), dd[2] | (dd[3] << 16));
+        uint32_t gw = nib << (4 * (lane & 7));        // OR over each group of 8 lanes (butterfly: all lanes in step)
+        gw |= __shfl_xor_sync(B200_FULL, gw, 1); gw |= __shfl_xor_sync(B200_FULL, gw, 2); gw |= __shfl_xor_sync(B200_FULL, gw, 4);
+        if ((lane & 7) == 0) s_mask[4 * buf + (lane >> 3)] = gw;
+    };
 
-    for (int s = 0; s < nchunks + 2; s++) {
-        if (isL) {
-            // ---------------- phase AB for chunk s
-            if (s < nchunks) {
-                const int c = s, cp0 = 128 * c - int(ph), buf = c & 1;
-                if (lane < 2) {
-                    const int pfq = cp0 + 512 + lane * 128;
-                    if (pfq < n) asm volatile("prefetch.global.L2 [%0];" :: "l"(__cvta_generic_to_global(src + pfq)));
-                }
-                const int p0 = cp0 + 4 * lane;
-                uint32_t w0 = 0, w1 = 0;
-                if (p0 + 3 >= 0 && p0 <= mflimit) { w0 = wsrc[32 * c + lane]; w1 = wsrc[32 * c + lane + 1]; }
-                uint32_t seq[4], h[4]; int cand[4]; bool plaus[4];
-                seq[0] = w0; seq[1] = __funnelshift_r(w0, w1, 8); seq[2] = __funnelshift_r(w0, w1, 16); seq[3] = __funnelshift_r(w0, w1, 24);
-                #pragma unroll
-                for (int j = 0; j < 4; j++) { h[j] = (seq[j] * 2654435761u) >> (32 - HASH_LOG); cand[j] = table[h[j]]; }
-                __syncwarp();  // every lookup of the chunk precedes every insert (same-slot stores: any winner is a valid position)
-                #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const int p = p0 + j;
-                    const bool valid = p >= 0 && p <= mflimit;
-                    // SPARSE: only one position in four is published (every position is still probed); a
-                    // half-size table then keeps about the same history (ratio -2..-5 %, twice the warps/SM)
-                    if (valid && (!SPARSE || j == 0)) table[h[j]] = Entry(p);
-                    plaus[j] = valid && cand[j] < p && (U16 || p - cand[j] <= 65535);
-                }
-                uint32_t cseq[4];
-                #pragma unroll
-                for (int j = 0; j < 4; j++) cseq[j] = plaus[j] ? ld4(cand[j]) : ~seq[j];
-                uint32_t nib = 0, dd[4];
-                #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const bool hit = cseq[j] == seq[j];
-                    dd[j] = hit ? uint32_t(p0 + j - cand[j]) : 0u;
-                    nib |= uint32_t(hit) << j;
-                }
-                reinterpret_cast<uint2*>(s_dist + 128 * buf)[lane] = make_uint2(dd[0] | (dd[1] << 16), dd[2] | (dd[3] << 16));
-                uint32_t gw = nib << (4 * (lane & 7));        // OR over each group of 8 lanes (butterfly: all lanes in step)
-                gw |= __shfl_xor_sync(B200_FULL, gw, 1); gw |= __shfl_xor_sync(B200_FULL, gw, 2); gw |= __shfl_xor_sync(B200_FULL, gw, 4);
-                if ((lane & 7) == 0) s_mask[4 * buf + (lane >> 3)] = gw;
-            }
-            // ---------------- write out the sequences of chunk s-2
-            if (s >= 2 && !fail) {
-                const int buf = s & 1;
-                const int cnt = s_cnt[buf];
-                SeqRec r = {0, 0, 0, 4};
-                if (lane < cnt) r = s_rec[32 * buf + lane];
-                const int lit = r.ms - r.anchor, mcode = r.ml - 4;
-                const int lhdr = lit >= 15 ? (lit - 15) / 255 + 1 : 0;
-                const int mhdr = mcode >= 15 ? (mcode - 15) / 255 + 1 : 0;
-                const int size = lane < cnt ? 1 + lhdr + lit + 2 + mhdr : 0;
-                int incl = size;
-                #pragma unroll
-                for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(B200_FULL, incl, d); if (lane >= d) incl += y; }
-                const int total = __shfl_sync(B200_FULL, incl, 31);
-                if (uint32_t(op) + uint32_t(total) > uint32_t(cap)) fail = true;                  // lz4.c:1085-1088, 1158
-                else {
-                    const int o = op + incl - size;
-                    if (lane < cnt) {
-                        uint8_t* d = dst + o;
-                        d[0] = uint8_t((min(lit, 15) << 4) | min(mcode, 15));
-                        d += 1;
-                        if (lit >= 15) { int v = lit - 15; for (; v >= 255; v -= 255) *d++ = 255; *d++ = uint8_t(v); }
-                        d += lit;
-                        d[0] = uint8_t(r.dist); d[1] = uint8_t(r.dist >> 8);                     // LE16 offset (lz4.c:1133)
-                        d += 2;
-                        if (mcode >= 15) { int v = mcode - 15; for (; v >= 255; v -= 255) *d++ = 255; *d++ = uint8_t(v); }
-                    }
-                    for (int k = 0; k < cnt; k++) {                                               // literal runs, one cooperative copy each
-                        const int ka = __shfl_sync(B200_FULL, r.anchor, k);
-                        const int kl = __shfl_sync(B200_FULL, lit, k);
-                        const int ko = __shfl_sync(B200_FULL, o + 1 + lhdr, k);
-                        warp_copy(dst + ko, src + ka, kl, lane);
-                    }
-                    op += total;
-                }
-            }
-        } else {
-            // ---------------- warp P: greedy walk of chunk s-1
-            if (s >= 1 && s <= nchunks) {
-                const int c = s - 1, cp0 = 128 * c - int(ph), buf = c & 1;
-                const unsigned long long hlo = (unsigned long long)s_mask[4 * buf] | ((unsigned long long)s_mask[4 * buf + 1] << 32);
-                const unsigned long long hhi = (unsigned long long)s_mask[4 * buf + 2] | ((unsigned long long)s_mask[4 * buf + 3] << 32);
-                int k = 0;
-                for (;;) {
-                    int r = ip - cp0;
-                    if (r < 0) r = 0;
-                    if (r >= 128) break;
-                    int q;
-                    {
-                        const unsigned long long lo = r < 64 ? (hlo >> r) : 0ull;
-                        if (lo) q = r + __ffsll((long long)lo) - 1;
-                        else {
-                            const int r2 = max(r - 64, 0);
-                            const unsigned long long hi = hhi >> r2;
-                            if (hi == 0) break;
-                            q = 64 + r2 + __ffsll((long long)hi) - 1;
-                        }
-                    }
-                    int ms = cp0 + q;
-                    const int dist = s_dist[128 * buf + q];
-                    const int mc = ms - dist;
-                    int ml;
-                    {
-                        const int d = lane - 8;
-                        const int backroom = min(ms - anchor, mc);
-                        const bool ok = d < 0 ? (-d <= backroom) : (ms + d < matchlimit);
-                        const bool eq = ok && src[ms + d] == src[mc + d];
-                        const unsigned e = __ballot_sync(B200_FULL, eq);
-                        const int back = __clz((~e) & 0xFFu) - 24;
-                        const int fwd = __ffs((~(e >> 8)) | (1u << 24)) - 1;
-                        ml = fwd;
-                        if (fwd == 24) ml += match_extend(InGlobal{src}, ms + 24, mc + 24, matchlimit - (ms + 24), lane);
-                        ms -= back; ml += back;
-                    }
-                    if (lane == 0) s_rec[32 * buf + k] = SeqRec{anchor, ms, dist, ml};
-                    k++;
-                    ip = anchor = ms + ml;
-                }
-                if (lane == 0) { s_cnt[buf] = k; s_cnt[2] = anchor; }
-            } else if (s > nchunks && lane == 0) {
-                s_cnt[(s - 1) & 1] = 0;          // nothing was parsed for this parity in the drain step
+    // ------------------------------------------------------------------ lay out the sequences of one chunk (warp E, or L)
+    int op = 0, prev_end = 0; bool fail = false;
+    auto emit = [&](int c) {
+        const int buf = c % NB;
+        const int cnt = s_cnt[buf];
+        uint2 r = make_uint2(0, 4);
+        if (lane < cnt) r = s_rec[32 * buf + lane];
+        const int ms = int(r.x & 0xFFFFu), dist = int(r.x >> 16), ml = int(r.y);
+        const int end = ms + ml;
+        int pe = __shfl_up_sync(B200_FULL, end, 1);
+        if (lane == 0) pe = prev_end;
+        const int lit = lane < cnt ? ms - pe : 0, mcode = ml - 4;
+        const int lhdr = lit >= 15 ? (lit - 15) / 255 + 1 : 0;
+        const int mhdr = mcode >= 15 ? (mcode - 15) / 255 + 1 : 0;
+        const int size = lane < cnt ? 1 + lhdr + lit + 2 + mhdr : 0;
+        int incl = size;
+        #pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(B200_FULL, incl, d); if (lane >= d) incl += y; }
+        const int total = __shfl_sync(B200_FULL, incl, 31);
+        if (cnt > 0) prev_end = __shfl_sync(B200_FULL, end, cnt - 1);
+        if (fail) return;
+        if (uint32_t(op) + uint32_t(total) > uint32_t(cap)) { fail = true; return; }              // lz4.c:1085-1088, 1158
+        const int o = op + incl - size;
+        if (lane < cnt) {
+            uint8_t* d = dst + o;
+            d[0] = uint8_t((min(lit, 15) << 4) | min(mcode, 15));
+            d += 1;
+            if (lit >= 15) { int v = lit - 15; for (; v >= 255; v -= 255) *d++ = 255; *d++ = uint8_t(v); }
+            d += lit;
+            d[0] = uint8_t(dist); d[1] = uint8_t(dist >> 8);                                     // LE16 offset (lz4.c:1133)
+            d += 2;
+            if (mcode >= 15) { int v = mcode - 15; for (; v >= 255; v -= 255) *d++ = 255; *d++ = uint8_t(v); }
+        }
+        // Literal runs: every lane copies the first 16 bytes of its own run (the runs of one chunk lie within a
+        // few lines of each other, so the 32 lanes' byte accesses coalesce); the rare longer runs are finished
+        // by the whole warp.
+        uint8_t* lo = dst + o + 1 + lhdr;
+        const int sn = min(lit, 16);
+        const int mx = __reduce_max_sync(B200_FULL, sn);
+        for (int t = 0; t < mx; t += 4) {
+            if (t < sn) {
+                const uint32_t v = ld4(pe + t);
+                lo[t] = uint8_t(v);
+                if (t + 1 < sn) lo[t + 1] = uint8_t(v >> 8);
+                if (t + 2 < sn) lo[t + 2] = uint8_t(v >> 16);
+                if (t + 3 < sn) lo[t + 3] = uint8_t(v >> 24);
             }
         }
-        asm volatile("bar.sync 1, 64;" ::: "memory");
-    }
-
-    if (isL) {
+        for (unsigned lm = __ballot_sync(B200_FULL, lit > 16); lm; lm &= lm - 1) {
+            const int k = __ffs(lm) - 1;
+            const int ka = __shfl_sync(B200_FULL, pe, k);
+            const int kl = __shfl_sync(B200_FULL, lit, k);
+            const int ko = __shfl_sync(B200_FULL, o + 1 + lhdr, k);
+            warp_copy(dst + ko + 16, src + ka + 16, kl - 16, lane);
+        }
+        op += total;
+    };
+    auto finish = [&]() {                                  // last literals (lz4.c:1266-1293)
         int ret = 0;
-        if (!fail) {   // last literals (lz4.c:1266-1293)
-            const int fin = s_cnt[2];
+        if (!fail) {
+            const int fin = prev_end;
             const int lit = n - fin;
             const int lhdr = lit >= 15 ? (lit - 15) / 255 + 1 : 0;
             if (uint32_t(op) + 1u + uint32_t(lhdr) + uint32_t(lit) <= uint32_t(cap)) {
@@ -584,19 +576,153 @@ lz4_compress_fast3_kernel(const uint8_t* __restrict__ src_base, const uint64_t* 
             }
         }
         if (lane == 0) result[b] = ret;
+    };
+
+    // ------------------------------------------------------------------ the greedy walk of one chunk (warp P)
+    int ip = 0, anchor = 0;
+    auto walk = [&](int c) {
+        const int cp0 = 128 * c - int(ph), buf = c % NB;
+        int k = 0;
+        const int r0 = max(ip - cp0, 0);
+        int nh = 0;
+        if (r0 < 128) {
+            #pragma unroll
+            for (int kk = 0; kk < 4; kk++) {                // rank the hits at or after ip: s_hit[rank] = position in chunk
+                uint32_t m = s_mask[4 * buf + kk];
+                const int lo = r0 - 32 * kk;
+                if (lo >= 32) m = 0; else if (lo > 0) m &= 0xFFFFFFFFu << lo;
+                if ((m >> lane) & 1u) s_hit[nh + __popc(m & ((1u << lane) - 1u))] = uint8_t(32 * kk + lane);
+                nh += __popc(m);
+            }
+        }
+        __syncwarp();
+        for (int done = 0; done < nh && ip < cp0 + 128; done += 32) {
+            const int idx = done + lane;
+            int ms = 0, ml = 0, back = 0, dist = 1; bool longer = false;
+            bool have = idx < nh;
+            if (have) { ms = cp0 + s_hit[idx]; have = ms >= ip; }
+            if (have) {
+                dist = s_dist[128 * buf + (ms - cp0)];
+                const int mc = ms - dist;
+                const int lim = matchlimit - ms, capl = min(lim, 32);
+                // One batch of loads covers the 4 bytes before and the 16 after the verified 4 on both sides (the
+                // candidate side misses L1 as a rule: one L2 round trip here instead of one per 4 bytes).
+                const uint32_t am = uint32_t(ms + 4) + ph, ac = uint32_t(mc + 4) + ph;     // +4: (pos - 4) never negative in the view
+                const uint32_t lastw = (uint32_t(n - 1) + ph) >> 2;
+                uint32_t wm[7], wc[7];
+                #pragma unroll
+                for (int t = 0; t < 7; t++) {
+                    wm[t] = wsrc[min((am >> 2) - 2 + t, lastw)];
+                    wc[t] = mc >= 4 ? wsrc[min((ac >> 2) - 2 + t, lastw)] : 0u;
+                }
+                const uint32_t sm = (am & 3u) * 8u, sc = (ac & 3u) * 8u;
+                if (mc >= 4) {
+                    const uint32_t x = __funnelshift_r(wm[0], wm[1], sm) ^ __funnelshift_r(wc[0], wc[1], sc);
+                    back = x ? (__clz(x) >> 3) : 4;
+                }
+                ml = 4;
+                if (mc >= 4) {
+                    #pragma unroll
+                    for (int t = 2; t < 6; t++) {
+                        const uint32_t x = __funnelshift_r(wm[t], wm[t + 1], sm) ^ __funnelshift_r(wc[t], wc[t + 1], sc);
+                        if (x) { ml += (__ffs(x) - 1) >> 3; goto measured; }
+                        ml += 4;
+                    }
+                }
+                while (ml < capl) {
+                    const uint32_t x = ld4(ms + ml) ^ ld4(mc + ml);
+                    if (x) { ml += (__ffs(x) - 1) >> 3; break; }
+                    ml += 4;
+                }
+            measured:
+                if (ml >= capl) { ml = capl; longer = capl < lim; }
+            }
+            // Hit positions are ranked, so the lanes' keys ascend: stale hits (before ip) sort to the front, empty
+            // lanes to the back.  succ(v) = first lane whose hit starts at or after v.
+            const int key = have ? ms : (idx < nh ? -1 : 0x7FFFFFFF);
+            const int key31 = __shfl_sync(B200_FULL, key, 31);
+            auto succ = [&](int v) -> int {
+                int q = 0;
+                #pragma unroll
+                for (int st = 16; st; st >>= 1) { const int pk = __shfl_sync(B200_FULL, key, q + st - 1); if (pk < v) q += st; }
+                if (q == 31 && key31 < v) q = 32;
+                return q;
+            };
+            int end = ms + ml;
+            const int nxt = succ(end);
+            const unsigned hm = __ballot_sync(B200_FULL, have);
+            const unsigned lm = __ballot_sync(B200_FULL, have && longer);
+            unsigned sel = 0;
+            int j = hm ? __ffs(hm) - 1 : 32;
+            while (j < 32 && ((hm >> j) & 1u)) {            // the greedy chain: one shuffle per selected sequence
+                sel |= 1u << j;
+                if ((lm >> j) & 1u) {                        // 32 bytes matched and more to go: finish with the whole warp
+                    const int jend = __shfl_sync(B200_FULL, end, j), jdist = __shfl_sync(B200_FULL, dist, j);
+                    const int ext = match_extend(InGlobal{src}, jend, jend - jdist, matchlimit - jend, lane);
+                    if (lane == j) { ml += ext; end += ext; }
+                    j = succ(jend + ext);
+                } else j = __shfl_sync(B200_FULL, nxt, j);
+            }
+            if (sel) {
+                const unsigned below = sel & ((1u << lane) - 1u);
+                int pend = __shfl_sync(B200_FULL, end, (31 - __clz(below)) & 31);     // end of the previous selected sequence
+                if (!below) pend = anchor;
+                if ((sel >> lane) & 1u) {
+                    const int bk = min(back, ms - pend);
+                    s_rec[32 * buf + k + __popc(below)] = make_uint2(uint32_t(ms - bk) | (uint32_t(dist) << 16), uint32_t(ml + bk));
+                }
+                k += __popc(sel);
+                ip = anchor = __shfl_sync(B200_FULL, end, 31 - __clz(sel));
+            }
+        }
+        if (lane == 0) s_cnt[buf] = k;
+    };
+
+    if (role == 0) {
+        for (int i = lane; i < TABLE_BYTES / 16; i += 32) reinterpret_cast<uint4*>(table)[i] = make_uint4(0, 0, 0, 0);
+        __syncwarp();
+        if (NW == 2) {
+            for (int i = 0; i < nchunks + LAG; i++) {
+                // chunk i's buffer is free: its previous tenant (chunk i-NB) was laid out in iteration i-1
+                if (i < nchunks) { lookup(i); bar_arrive(BAR_FULL + i % NB); }
+                if (i >= LAG) { bar_wait(BAR_WALKED + (i - LAG) % NB); emit(i - LAG); }
+            }
+            finish();
+        } else {
+            for (int c = 0; c < nchunks; c++) {
+                if (c >= NB) bar_wait(BAR_DFREE + c % NB);                      // warp P is done with chunk c-NB's distances
+                lookup(c);
+                bar_arrive(BAR_FULL + c % NB);
+            }
+        }
+    } else if (role == 1) {
+        for (int c = 0; c < nchunks; c++) {
+            bar_wait(BAR_FULL + c % NB);
+            if (NW == 3 && c >= NB) bar_wait(BAR_RFREE + c % NB);               // warp E is done with chunk c-NB's records
+            walk(c);
+            bar_arrive(BAR_WALKED + c % NB);
+            if (NW == 3 && c + NB < nchunks) bar_arrive(BAR_DFREE + c % NB);
+        }
+    } else {
+        for (int c = 0; c < nchunks; c++) {
+            bar_wait(BAR_WALKED + c % NB);
+            emit(c);
+            if (c + NB < nchunks) bar_arrive(BAR_RFREE + c % NB);
+        }
+        finish();
     }
 }
 
-template <int HASH_LOG, bool U16, bool SPARSE>
+template <int HASH_LOG, bool SPARSE>
 static cudaError_t launch_v3(const BatchArgs& a, cudaStream_t st)
 {
-    const size_t smem = ((U16 ? 2u : 4u) << HASH_LOG) + 512 + 1024 + 32 + 16;
-    auto k = lz4_compress_fast3_kernel<HASH_LOG, U16, SPARSE>;
+    const size_t smem = (2u << HASH_LOG) + B200_V3_NB * (256 + 256 + 16) + 16 + 128;
+    auto k = lz4_compress_fast3_kernel<HASH_LOG, SPARSE>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    k<<<(unsigned)a.n, 64, smem, st>>>(a.src_base, a.src_off, a.src_len, a.dst_base, a.dst_off, a.dst_cap,
-                                       a.result, (uint32_t)a.n);
+    k<<<(unsigned)a.n, 32 * B200_V3_WARPS, smem, st>>>(a.src_base, a.src_off, a.src_len, a.dst_base, a.dst_off, a.dst_cap,
+                                                        a.result, (uint32_t)a.n);
     return cudaGetLastError();
 }
 
@@ -923,9 +1049,9 @@ cudaError_t launch_compress_fast(const BatchArgs& a, int max_src_len, cudaStream
         return b200lz4_compress_sparse ? launch_v4<13, true>(a, st) : launch_v4<13, false>(a, st);
     }
     if ((b200lz4_compress_algo == 3 || b200lz4_compress_algo == 4) && !b200lz4_compress_stage) {
-        if (!u16) return launch_v3<12, false, false>(a, st);
-        if (b200lz4_compress_hash_log == 12) return b200lz4_compress_sparse ? launch_v3<12, true, true>(a, st) : launch_v3<12, true, false>(a, st);
-        return b200lz4_compress_sparse ? launch_v3<13, true, true>(a, st) : launch_v3<13, true, false>(a, st);
+        if (!u16) return launch_v2<12, false>(a, st);          // blocks > 64 KiB: one-warp decoupled parser with the 32-bit table
+        if (b200lz4_compress_hash_log == 12) return b200lz4_compress_sparse ? launch_v3<12, true>(a, st) : launch_v3<12, false>(a, st);
+        return b200lz4_compress_sparse ? launch_v3<13, true>(a, st) : launch_v3<13, false>(a, st);
     }
     if (b200lz4_compress_algo == 2 && !b200lz4_compress_stage) {
         if (!u16) return launch_v2<12, false>(a, st);

@@ -53,7 +53,10 @@ def main():
         ctypes.c_int.in_dll(lib, "b200lz4_compress_algo").value = algo
         t, med = timeit(lambda: B.compress_fast_batch_dev(src, soff, slen, comp, coff, ccap, clen, bs))
         C = int(clen.sum().item())
-        print(f"compress hl={hl} stage={stage} algo={algo} sparse={sparse}: {N/t/2**30:.1f} GiB/s best ({N/med/2**30:.1f} med)  ratio {N/C:.3f}  hbm {(N+C)/t/1e9:.0f} GB/s", flush=True)
+        out.zero_(); B.decompress_safe_batch_dev(comp, coff, clen, out, soff, slen, res)
+        rt = bool((res == bs).all().item()) and bool(torch.equal(out, src))
+        print(f"compress hl={hl} stage={stage} algo={algo} sparse={sparse}: {N/t/2**30:.1f} GiB/s best ({N/med/2**30:.1f} med)  ratio {N/C:.3f}  hbm {(N+C)/t/1e9:.0f} GB/s  roundtrip={rt}", flush=True)
+    if os.environ.get("COMPRESS_ONLY"): return
     t, med = timeit(lambda: B.decompress_safe_batch_dev(comp, coff, clen, out, soff, slen, res))
     ok = bool((res == bs).all().item()) and bool(torch.equal(out, src))
     print(f"decompress_safe: {N/t/2**30:.1f} GiB/s best ({N/med/2**30:.1f} med) ok={ok}  hbm {(N+C)/t/1e9:.0f} GB/s", flush=True)
