@@ -32,6 +32,8 @@ struct FrameRec {
     uint32_t content_checksum; bool has_checksum;
     uint64_t out_off;                   // slot-layout start of this frame's content
 };
+static constexpr uint64_t XXH_LONG_AVG = 32768;     // average stream length from which a whole warp per stream wins
+
 struct BlockRec { uint64_t src_off; uint32_t size; bool raw; uint32_t checksum; bool has_checksum; size_t frame; uint64_t out_off; };
 
 struct FrameIndex {
@@ -194,8 +196,11 @@ int64_t b200lz4f_decode_dev(void* index, const uint8_t* d_src, uint8_t* d_slots,
     g_launch_count += 1;
     if (launch_xxh32(d_src, (uint64_t*)(D + ix.o_h_off), (int32_t*)(D + ix.o_h_len), 0, (uint32_t*)(D + ix.o_h_out), nf, st) != cudaSuccess) return B200LZ4_E_CUDA;
     if (ix.n_bsum) {
+        // few long payloads: one warp per stream; many short ones: one lane per buffer (xxhash.cu)
+        uint64_t sum = 0; for (size_t k = 0; k < ix.n_bsum; k++) sum += ix.blocks[ix.bsum_ix[k]].size;
         g_launch_count += 1;
-        if (launch_xxh32(d_src, (uint64_t*)(D + ix.o_b_off), (int32_t*)(D + ix.o_b_len), 0, (uint32_t*)(D + ix.o_b_out), ix.n_bsum, st) != cudaSuccess) return B200LZ4_E_CUDA;
+        if ((sum / ix.n_bsum >= XXH_LONG_AVG ? launch_xxh32_long : launch_xxh32)(
+                d_src, (uint64_t*)(D + ix.o_b_off), (int32_t*)(D + ix.o_b_len), 0, (uint32_t*)(D + ix.o_b_out), ix.n_bsum, st) != cudaSuccess) return B200LZ4_E_CUDA;
     }
     // 2. blocks
     if (ix.n_comp) {
@@ -243,16 +248,19 @@ int64_t b200lz4f_decode_dev(void* index, const uint8_t* d_src, uint8_t* d_slots,
     if (gaps) return -11;
     // 3. content checksums over each frame's (contiguous) content
     if (ix.n_fsum) {
+        uint64_t sum = 0;
         for (size_t k = 0; k < ix.n_fsum; k++) {
             const FrameRec& fr = ix.frames[ix.fsum_ix[k]];
             uint64_t len = 0; for (size_t j = 0; j < fr.nblocks; j++) len += (uint64_t)blen[fr.first_block + j];
-            if (len > 0x7FFFFFFFull) return -10;                              // one lane hashes one frame; >2 GiB frames are not indexed as one buffer
+            if (len > 0x7FFFFFFFull) return -10;                              // >2 GiB frames are not indexed as one buffer
+            sum += len;
             ((uint64_t*)(H + ix.o_f_off))[k] = fr.out_off; ((int32_t*)(H + ix.o_f_len))[k] = (int32_t)len;
         }
         if (cudaMemcpyAsync(D + ix.o_f_off, H + ix.o_f_off, ix.n_fsum * 8, cudaMemcpyHostToDevice, st) != cudaSuccess) return B200LZ4_E_CUDA;
         if (cudaMemcpyAsync(D + ix.o_f_len, H + ix.o_f_len, ix.n_fsum * 4, cudaMemcpyHostToDevice, st) != cudaSuccess) return B200LZ4_E_CUDA;
         g_launch_count += 1;
-        if (launch_xxh32(d_slots, (uint64_t*)(D + ix.o_f_off), (int32_t*)(D + ix.o_f_len), 0, (uint32_t*)(D + ix.o_f_out), ix.n_fsum, st) != cudaSuccess) return B200LZ4_E_CUDA;
+        if ((sum / ix.n_fsum >= XXH_LONG_AVG ? launch_xxh32_long : launch_xxh32)(
+                d_slots, (uint64_t*)(D + ix.o_f_off), (int32_t*)(D + ix.o_f_len), 0, (uint32_t*)(D + ix.o_f_out), ix.n_fsum, st) != cudaSuccess) return B200LZ4_E_CUDA;
         if (cudaMemcpyAsync(H + ix.o_f_out, D + ix.o_f_out, ix.n_fsum * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) return B200LZ4_E_CUDA;
         if (cudaStreamSynchronize(st) != cudaSuccess) return B200LZ4_E_CUDA;
         for (size_t k = 0; k < ix.n_fsum; k++)

@@ -24,6 +24,9 @@ cudaError_t launch_compress_fast(const BatchArgs& a, int max_src_len, cudaStream
 cudaError_t launch_compress_hc(const BatchArgs& a, int level, cudaStream_t st);
 cudaError_t launch_xxh32(const uint8_t* base, const uint64_t* off, const int32_t* len, uint32_t seed,
                          uint32_t* out, size_t n, cudaStream_t st);
+// One warp per buffer: for a few long streams (frame content checksums).
+cudaError_t launch_xxh32_long(const uint8_t* base, const uint64_t* off, const int32_t* len, uint32_t seed,
+                              uint32_t* out, size_t n, cudaStream_t st);
 cudaError_t launch_xxh64(const uint8_t* base, const uint64_t* off, const int32_t* len, uint64_t seed,
                          uint64_t* out, size_t n, cudaStream_t st);
 

@@ -208,33 +208,142 @@ cudaError_t launch_xxh64(const uint8_t* base, const uint64_t* off, const int32_t
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------ one long XXH32 stream per warp
+// A single XXH32 stream is four serial accumulator chains (xxhash.c:269-275: acc = rotl(acc + w*P2, 13) * P1,
+// ~10 cycles per 16-byte stripe), so one stream cannot go faster than ~3 GB/s on this clock whatever feeds it.
+// The batch kernel above gives every lane its own buffer — right for millions of small buffers, wrong for a
+// handful of large ones (32 frames of 64 MiB would sit in ONE warp).  Here a whole warp feeds one stream:
+// rows of 128 bytes are loaded coalesced (one word per lane), two groups of 8 rows in flight, and every lane
+// runs chain (lane & 3) on words pulled out of the row registers by shuffle (word j of stripe s sits in lane
+// 4*s + j).  All eight lane quads compute the same four chains, so the result is valid on every lane.
+// Long streams then scale with the number of streams: one warp (one SM) each.
+__device__ __forceinline__ uint32_t xxh32_chain_init(uint32_t seed, int lane)
+{
+    const int c = lane & 3;
+    return c == 0 ? seed + P32_1 + P32_2 : c == 1 ? seed + P32_2 : c == 2 ? seed : seed - P32_1;
+}
+
+// Consume `rows` rows of 128 bytes starting at p (any alignment) into this lane's chain.
+__device__ __forceinline__ uint32_t xxh32_warp_rows(uint32_t v, const uint8_t* __restrict__ p, size_t rows, int lane)
+{
+    constexpr int R = 8;
+    const uintptr_t sa = reinterpret_cast<uintptr_t>(p);
+    const uint32_t* __restrict__ W = reinterpret_cast<const uint32_t*>(sa & ~uintptr_t(3));
+    const uint32_t sh = (uint32_t(sa) & 3u) * 8u;
+    const int c = lane & 3;
+    auto ldrow = [&](size_t r) -> uint32_t {
+        const size_t i = r * 32 + lane;
+        const uint32_t a = W[i];
+        return sh ? __funnelshift_r(a, W[i + 1], sh) : a;
+    };
+    uint32_t cur[R], nxt[R];
+    const size_t groups = rows / R;
+    if (groups) {
+        #pragma unroll
+        for (int r = 0; r < R; r++) cur[r] = ldrow(r);
+    }
+    for (size_t g = 0; g < groups; g++) {
+        if (g + 1 < groups) {
+            #pragma unroll
+            for (int r = 0; r < R; r++) nxt[r] = ldrow((g + 1) * R + r);
+        }
+        #pragma unroll
+        for (int r = 0; r < R; r++) {
+            #pragma unroll
+            for (int st = 0; st < 8; st++) v = round32(v, __shfl_sync(B200_FULL, cur[r], 4 * st + c));
+        }
+        #pragma unroll
+        for (int r = 0; r < R; r++) cur[r] = nxt[r];
+    }
+    for (size_t r = groups * R; r < rows; r++) {
+        const uint32_t x = ldrow(r);
+        #pragma unroll
+        for (int st = 0; st < 8; st++) v = round32(v, __shfl_sync(B200_FULL, x, 4 * st + c));
+    }
+    return v;
+}
+
+// All stripes of [p, p + 16*stripes): rows by the warp, the last < 8 stripes by direct loads.
+__device__ __forceinline__ uint32_t xxh32_warp_stripes(uint32_t v, const uint8_t* __restrict__ p, size_t stripes, int lane)
+{
+    const size_t rows = stripes >> 3;
+    v = xxh32_warp_rows(v, p, rows, lane);
+    for (size_t t = rows << 3; t < stripes; t++) v = round32(v, load_u32_unaligned(p + 16 * t + 4 * (lane & 3)));
+    return v;
+}
+
+__device__ __forceinline__ uint32_t xxh32_chain_merge(uint32_t v)
+{
+    return rotl32(__shfl_sync(B200_FULL, v, 0), 1) + rotl32(__shfl_sync(B200_FULL, v, 1), 7) +
+           rotl32(__shfl_sync(B200_FULL, v, 2), 12) + rotl32(__shfl_sync(B200_FULL, v, 3), 18);
+}
+
+__global__ void __launch_bounds__(32)
+xxh32_long_kernel(const uint8_t* __restrict__ base, const uint64_t* __restrict__ off, const int32_t* __restrict__ len,
+                  uint32_t seed, uint32_t* __restrict__ out, uint32_t n)
+{
+    const uint32_t i = blockIdx.x;
+    if (i >= n) return;
+    const int lane = lane_id();
+    const uint8_t* __restrict__ p = base + off[i];
+    const uint32_t L = (uint32_t)max(len[i], 0);
+    const size_t stripes = L >> 4;
+    uint32_t h;
+    if (L >= 16u) h = xxh32_chain_merge(xxh32_warp_stripes(xxh32_chain_init(seed, lane), p, stripes, lane));
+    else h = seed + P32_5;
+    if (lane == 0) out[i] = finish32(h + L, p + 16 * stripes, L & 15u);
+}
+
+cudaError_t launch_xxh32_long(const uint8_t* base, const uint64_t* off, const int32_t* len, uint32_t seed,
+                              uint32_t* out, size_t n, cudaStream_t st)
+{
+    if (n == 0) return cudaSuccess;
+    xxh32_long_kernel<<<(unsigned)n, 32, 0, st>>>(base, off, len, seed, out, (uint32_t)n);
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------ streaming state (device-resident)
 // One lane walks the XXH32_update / XXH64_update state machine (xxhash.c:515-546, 971-1002); the
 // serial dependency makes more lanes pointless.  reset / digest are the same kernel with op codes.
 __global__ void xxh32_stream_kernel(Xxh32State* s, int op, uint32_t seed, const uint8_t* __restrict__ p, size_t len)
 {
-    if (threadIdx.x != 0) return;
+    const int lane = lane_id();
     if (op == XXH_OP_RESET) {
+        if (lane) return;
         s->total = 0; s->memsize = 0; s->seed = seed;
         s->v[0] = seed + P32_1 + P32_2; s->v[1] = seed + P32_2; s->v[2] = seed; s->v[3] = seed - P32_1;
         return;
     }
     if (op == XXH_OP_UPDATE) {
-        const uint8_t* end = p + len;
-        s->total += len;
-        if (s->memsize + len < 16) { for (size_t i = 0; i < len; i++) s->mem[s->memsize + i] = p[i]; s->memsize += (uint32_t)len; return; }
-        Acc<32> a; a.v1 = s->v[0]; a.v2 = s->v[1]; a.v3 = s->v[2]; a.v4 = s->v[3];
-        if (s->memsize) {
-            const uint32_t fill = 16 - s->memsize;
-            for (uint32_t i = 0; i < fill; i++) s->mem[s->memsize + i] = p[i];
-            a.stripe_g(s->mem); p += fill; s->memsize = 0;
+        // XXH32_update (xxhash.c:515-546) with the stripe loop spread over the warp (xxh32_warp_stripes); the state is
+        // read by every lane (uniform control flow) and written back by lanes 0-3 / lane 0.
+        const uint32_t memsize = s->memsize;
+        const uint64_t total = s->total;
+        uint32_t v = s->v[lane & 3];
+        __syncwarp();
+        if (memsize + len < 16) {
+            if (lane == 0) { for (size_t i = 0; i < len; i++) s->mem[memsize + i] = p[i]; s->memsize = memsize + (uint32_t)len; s->total = total + len; }
+            return;
         }
-        while (p + 16 <= end) { a.stripe_g(p); p += 16; }
-        s->v[0] = a.v1; s->v[1] = a.v2; s->v[2] = a.v3; s->v[3] = a.v4;
-        uint32_t r = 0; while (p < end) s->mem[r++] = *p++;
-        s->memsize = r;
+        if (memsize) {
+            const uint32_t fill = 16 - memsize;
+            if (lane == 0) for (uint32_t i = 0; i < fill; i++) s->mem[memsize + i] = p[i];
+            __syncwarp();
+            v = round32(v, load_u32_unaligned(s->mem + 4 * (lane & 3)));
+            p += fill; len -= fill;
+            __syncwarp();
+        }
+        const size_t stripes = len >> 4;
+        v = xxh32_warp_stripes(v, p, stripes, lane);
+        if (lane < 4) s->v[lane] = v;
+        if (lane == 0) {
+            const uint32_t r = (uint32_t)(len & 15);
+            for (uint32_t i = 0; i < r; i++) s->mem[i] = p[16 * stripes + i];
+            s->memsize = r; s->total = total + (memsize ? 16 - memsize : 0) + len;
+        }
         return;
     }
+    if (lane) return;
     {   // digest (xxhash.c:548-563): non-destructive
         uint32_t h;
         if (s->total >= 16) h = rotl32(s->v[0], 1) + rotl32(s->v[1], 7) + rotl32(s->v[2], 12) + rotl32(s->v[3], 18);

@@ -20,7 +20,19 @@ def _slots(lens, extra=0, align=16):
     return np.array(offs, dtype=np.uint64), np.array(caps, dtype=np.int32), pos + 64
 
 
-def test_decompress_safe_exact(b200, checker):
+@pytest.fixture(params=["batched", "sequential"])
+def decoder(request, b200):
+    """Both builds of the decoders on the same inputs: decode_batch() in front (few / large blocks) and the
+    one-sequence-at-a-time kernels (the library picks by batch size; the knob forces one)."""
+    import ctypes
+    knob = ctypes.c_int.in_dll(b200._native.lib(), "b200lz4_decompress_batch_below")
+    old = knob.value
+    knob.value = (1 << 30) if request.param == "batched" else 0
+    yield request.param
+    knob.value = old
+
+
+def test_decompress_safe_exact(b200, checker, decoder):
     items = corpus.blocks(checker) + corpus.calgary_blocks()
     comp = [checker.compress(d) for _, d in items]
     src, soff, slen = corpus.pack(comp)
@@ -34,7 +46,7 @@ def test_decompress_safe_exact(b200, checker):
         assert (dst[int(doff[k]) + len(d):int(doff[k]) + len(d) + 16] == 0xAA).all(), name
 
 
-def test_decompress_fast_exact(b200, checker):
+def test_decompress_fast_exact(b200, checker, decoder):
     items = corpus.blocks(checker) + corpus.calgary_blocks()
     comp = [checker.compress(d) for _, d in items]
     src, soff, slen = corpus.pack(comp)
@@ -47,7 +59,7 @@ def test_decompress_fast_exact(b200, checker):
         assert (dst[int(doff[k]) + len(d):int(doff[k]) + len(d) + 16] == 0xAA).all(), name
 
 
-def test_decompress_safe_malformed_codes(b200, checker):
+def test_decompress_safe_malformed_codes(b200, checker, decoder):
     """Same accept/reject set AND same negative codes as the reference (lz4.c:2337)."""
     rng = random.Random(99)
     cases = []                                           # (compressed bytes, capacity)
@@ -82,7 +94,7 @@ def test_decompress_safe_malformed_codes(b200, checker):
     assert negatives > 100
 
 
-def test_decompress_fast_malformed(b200, checker):
+def test_decompress_fast_malformed(b200, checker, decoder):
     rng = random.Random(7)
     cases = []
     for name, d in corpus.blocks(checker, big=False):
@@ -107,6 +119,53 @@ def test_decompress_fast_malformed(b200, checker):
         assert res[k] == want, (k, len(c), dl, int(res[k]), want)
         if want >= 0:
             assert dst[int(doff[k]):int(doff[k]) + dl].tobytes() == out, k
+
+
+def test_decompress_dependency_patterns(b200, checker, decoder):
+    """Streams built to stress the batched decoder's match rounds: runs (offset 1), short periods, matches
+    whose source is the previous sequence's output, long literal runs and long matches, all mixed."""
+    rng = random.Random(4242)
+    items = []
+    for trial in range(24):
+        parts = []
+        while sum(map(len, parts)) < 30000 + 4000 * trial:
+            kind = rng.randrange(7)
+            if kind == 0:
+                parts.append(bytes([rng.randrange(256)]) * rng.randrange(5, 700))                      # run
+            elif kind == 1:
+                pat = bytes(rng.randrange(256) for _ in range(rng.randrange(2, 9)))
+                parts.append(pat * rng.randrange(3, 120))                                              # short period
+            elif kind == 2:
+                parts.append(bytes(rng.randrange(256) for _ in range(rng.randrange(1, 80))))           # literals
+            elif kind == 3 and parts:
+                prev = b"".join(parts[-3:])
+                a = rng.randrange(len(prev)); parts.append(prev[a:a + rng.randrange(4, 60)])           # near copy
+            elif kind == 4 and parts:
+                whole = b"".join(parts)
+                a = rng.randrange(len(whole)); parts.append(whole[a:a + rng.randrange(4, 400)])        # far copy
+            elif kind == 5:
+                pat = bytes(rng.randrange(256) for _ in range(rng.randrange(33, 200)))
+                parts.append(pat * rng.randrange(2, 6))                                                # period >= 32
+            else:
+                parts.append(bytes(rng.randrange(4) for _ in range(rng.randrange(20, 300))))           # low entropy
+        items.append(b"".join(parts))
+    comp = [checker.compress(d) for d in items]
+    src, soff, slen = corpus.pack(comp)
+    doff, dcap, total = _slots([len(d) for d in items], extra=3)
+    for fast in (False, True):
+        dst = np.full(total, 0x55, dtype=np.uint8)
+        if fast:
+            lens = np.array([len(d) for d in items], dtype=np.int32)
+            res = b200.batch.decompress_fast_batch_host(src, soff, slen, dst, doff, lens)
+        else:
+            res = b200.batch.decompress_safe_batch_host(src, soff, slen, dst, doff, dcap)
+        for k, d in enumerate(items):
+            assert res[k] == (len(comp[k]) if fast else len(d)), (decoder, fast, k, int(res[k]))
+            assert dst[int(doff[k]):int(doff[k]) + len(d)].tobytes() == d, (decoder, fast, k)
+            # bytes between the decoded length and the slot capacity are unspecified (as with the reference's wild
+            # copies); nothing may be written past the capacity
+            end = int(doff[k]) + (len(d) if fast else int(dcap[k]))
+            assert (dst[end:end + 13] == 0x55).all(), (decoder, fast, k)
 
 
 def _knob(b200, name, value):
@@ -243,6 +302,30 @@ def test_xxhash_uniform_4k(b200, checker):
         blk = data[k * 4096:(k + 1) * 4096]
         assert int(h64[k]) == checker.xxh64(blk, 0)
         assert int(h32[k]) == checker.xxh32(blk, 0x9747B28C)
+
+
+def test_xxhash32_long_streams(b200, checker):
+    """a few long buffers take the one-warp-per-stream kernel: every alignment phase, every tail length"""
+    rng = random.Random(21)
+    blob = np.frombuffer(rng.randbytes(6 << 20), dtype=np.uint8).copy()
+    offs, lens, pos = [], [], 0
+    for k in range(9):
+        pos += rng.randrange(0, 9)                                   # alignment phase 0..3 and beyond
+        n = rng.choice([32768, 40000, 65536 + k, 300000 + 17 * k, 1 << 20]) + rng.randrange(0, 16)
+        n = min(n, len(blob) - pos)
+        offs.append(pos); lens.append(n); pos += n
+    off = np.array(offs, dtype=np.uint64); ln = np.array(lens, dtype=np.int32)
+    for seed in (0, 0x9747B28C):
+        h = b200.batch.xxh32_batch_host(blob, off, ln, seed)
+        for k in range(len(offs)):
+            assert int(h[k]) == checker.xxh32(blob[offs[k]:offs[k] + lens[k]], seed), (k, offs[k], lens[k])
+    # the streaming state takes the same warp loop for large updates
+    f = b200.XXHashFactory.b200Instance()
+    data = blob[3:3 + (1 << 20) + 5].tobytes()
+    h = f.newStreamingHash32(7)
+    h.update(data, 0, 5); h.update(data, 5, 70001); h.update(data, 70006, len(data) - 70006)
+    assert h.getValue() == checker.xxh32(data, 7)
+    h.close()
 
 
 def test_xxhash_streaming(b200, checker):

@@ -86,15 +86,18 @@ def config3(chk, out):
     total = nframes * fsize
     # end to end with host buffers
     outbuf = np.empty(total, dtype=np.uint8)
-    t1 = time.perf_counter()
-    r = lib.b200lz4f_decompress_host(host.ctypes.data, len(host), outbuf.ctypes.data, total)
-    te = time.perf_counter() - t1
+    te = 1e30
+    for _ in range(2):                                  # first call allocates the thread's staging buffers
+        t1 = time.perf_counter()
+        r = lib.b200lz4f_decompress_host(host.ctypes.data, len(host), outbuf.ctypes.data, total)
+        te = min(te, time.perf_counter() - t1)
     assert r == total and (outbuf[:fsize] == one).all() and (outbuf[-fsize:] == one).all()
     out["config3_frame_decode"] = {"frames": nframes, "frame_MiB": fsize >> 20, "block": "4 MiB independent, content checksum",
                                    "device_resident_GiBps": total / t / GIB, "end_to_end_host_GiBps": total / te / GIB,
                                    "blocks": int(lib.b200lz4f_index_blocks(index)),
                                    "note": "device time includes header/content XXH32 verification and two host syncs for sizes/checksums; "
-                                           "content hash = one lane per frame (XXH32 is a serial chain per frame)"}
+                                           "blocks go through the batched decoder (32 sequences in flight per warp), content hash = one warp per frame "
+                                           "(XXH32 is four serial chains per stream: ~3 GB/s per frame, frames in parallel)"}
     lib.b200lz4f_index_free(index)
 
 

@@ -1,5 +1,5 @@
 #!/bin/bash
-# Build alternative libb200lz4.so files with different compile-time knobs of the two-warp compress kernel
+# Build alternative libb200lz4.so files with different compile-time knobs of the compress / decompress kernels
 # (for A/B probes on the GPU box: B200LZ4_SO=variants/libb200lz4_<name>.so python tools/probe.py).
 # usage: tools/build_variants.sh name:"-DFLAG=.. -DFLAG=.." ...
 set -e
@@ -8,7 +8,9 @@ make -j8 >/dev/null
 ARCH="-gencode arch=compute_100a,code=sm_100a"
 for spec in "$@"; do
   name="${spec%%:*}"; flags="${spec#*:}"
-  nvcc -std=c++17 -O3 -lineinfo $ARCH -Xcompiler -fPIC --expt-relaxed-constexpr $flags -c lz4_compress.cu -o /tmp/lz4_compress_$name.o
-  nvcc $ARCH -shared -o ../../variants/libb200lz4_$name.so capi.o lz4_decompress.o /tmp/lz4_compress_$name.o lz4hc_compress.o xxhash.o compact.o frame.o containers.o
+  for f in lz4_compress lz4_decompress; do
+    nvcc -std=c++17 -O3 -lineinfo $ARCH -Xcompiler -fPIC --expt-relaxed-constexpr $flags -c $f.cu -o /tmp/${f}_$name.o
+  done
+  nvcc $ARCH -shared -o ../../variants/libb200lz4_$name.so capi.o /tmp/lz4_decompress_$name.o /tmp/lz4_compress_$name.o lz4hc_compress.o xxhash.o compact.o frame.o containers.o
   echo "built variants/libb200lz4_$name.so ($flags)"
 done

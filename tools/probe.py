@@ -43,6 +43,8 @@ def main():
     N = nblk * bs
     import ctypes
     lib = L._native.lib()
+    if os.environ.get("DEC_BELOW"):
+        ctypes.c_int.in_dll(lib, "b200lz4_decompress_batch_below").value = int(os.environ["DEC_BELOW"])
     variants = os.environ.get("VARIANTS", "13:0:3,12:0:3,13:0:2,12:0:2,13:0:1")
     for v in variants.split(","):
         parts = v.split(":") + ["3", "0"]
