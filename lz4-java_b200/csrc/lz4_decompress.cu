@@ -30,6 +30,10 @@ namespace b200 {
 #ifndef B200_DEC_MINB_BATCH
 #define B200_DEC_MINB_BATCH 8
 #endif
+#ifndef B200_DEC_WIN
+#define B200_DEC_WIN 512
+#endif
+static constexpr int DEC_WIN = B200_DEC_WIN;   // bytes of compressed stream one batch looks at (16 per lane)
 #ifndef B200_DEC_BATCH_BELOW
 #define B200_DEC_BATCH_BELOW 0x7FFFFFFF
 #endif
@@ -56,9 +60,9 @@ __device__ __forceinline__ VarLen read_varlen(const uint8_t* __restrict__ src, i
 //
 // A lone warp that decodes one sequence after another pays one L2 round trip per sequence (the match
 // source is the block's own fresh output, which L1 does not hold).  Here the warp
-//   1. loads a 256-byte window of the compressed stream (8 bytes per lane) and walks the token chain
-//      on warp-uniform values — window bytes come from registers by shuffle, so a step is ALU work,
-//      not a load; lane k keeps the fields of sequence k;
+//   1. stages a 512-byte window of the compressed stream in shared memory (16 bytes per lane) and walks the
+//      token chain on warp-uniform values — a step costs one LDS, not a global load; lane k keeps the fields
+//      of sequence k;
 //   2. turns lengths into output offsets with one prefix sum, reads the 32 match offsets in parallel;
 //   3. copies all literal runs at once (first 16 bytes by the owning lane, the rest cooperatively);
 //   4. copies the matches in dependency rounds: a match is ready when its source lies below the output
@@ -91,30 +95,35 @@ __device__ __forceinline__ void lane_copy16(uint8_t* d, const uint8_t* s, int n)
 }
 
 __device__ __forceinline__ int decode_batch(const uint8_t* __restrict__ src, uint8_t* dst, int& ip, int& op,
-                                            const int iend, const int oend, const int lane)
+                                            const int iend, const int oend, const int lane, uint8_t* win)
 {
+    // window: DEC_WIN compressed bytes from ip (16 per lane), staged in this warp's slice of shared memory so that the
+    // walk reads a byte with one LDS (from registers by shuffle it took 8 instructions per byte — most of the parse)
     const uint8_t* __restrict__ in = src + ip;
-    const uintptr_t base = reinterpret_cast<uintptr_t>(in);
-    const uint32_t* __restrict__ W = reinterpret_cast<const uint32_t*>(base & ~uintptr_t(3));
-    const uint32_t a8 = (uint32_t(base) & 3u) * 8u;
-    const uint32_t w0 = W[2 * lane], w1 = W[2 * lane + 1], w2 = W[2 * lane + 2];
-    const uint32_t lo = __funnelshift_r(w0, w1, a8), hi = __funnelshift_r(w1, w2, a8);   // window bytes [8*lane, 8*lane+8)
-    auto wbyte = [&](int q) -> uint32_t {                    // q is warp-uniform
-        if (q < 256) return (__shfl_sync(B200_FULL, (q & 4) ? hi : lo, q >> 3) >> ((q & 3) * 8)) & 255u;
-        return in[q];
-    };
+    {
+        const uintptr_t base = reinterpret_cast<uintptr_t>(in);
+        const uint32_t* __restrict__ W = reinterpret_cast<const uint32_t*>(base & ~uintptr_t(3)) + 4 * lane;
+        const uint32_t a8 = (uint32_t(base) & 3u) * 8u;
+        const uint32_t w0 = W[0], w1 = W[1], w2 = W[2], w3 = W[3], w4 = W[4];
+        __syncwarp();                                        // the previous window is no longer read
+        reinterpret_cast<uint4*>(win)[lane] = make_uint4(__funnelshift_r(w0, w1, a8), __funnelshift_r(w1, w2, a8),
+                                                         __funnelshift_r(w2, w3, a8), __funnelshift_r(w3, w4, a8));
+        __syncwarp();
+    }
+    auto wbyte = [&](int q) -> uint32_t { return q < DEC_WIN ? win[q] : in[q]; };
     const int ilim = iend - ip - 64;                         // a sequence must end at or before in[ilim]
     const int olim = oend - op - 128;                        // ... and its output at or before dst[op + olim]
+    const bool roomy = olim >= 32 * 33;                      // 32 plain sequences (<= 33 bytes each) cannot reach olim
 
     // ---- 1. token chain.  Lane k keeps where sequence k's token is and where its output starts; the common
     // token (no length extension) is decoded after the walk, by all lanes at once.
     int k = 0, q = 0, acc = 0;
     int m_tok = 0, m_out = 0, m_lsrc = 0, m_lit = -1, m_ml = 0;
-    while (k < 32 && q < 248) {
-        const uint32_t tok = wbyte(q);
+    while (k < 32 && q < DEC_WIN - 8) {
+        const uint32_t tok = win[q];
         uint32_t lit = tok >> 4, ml = tok & 15u;
-        if (lit != 15 && ml != 15) {                          // ends within the window's margin by construction (384-byte precondition)
-            if (acc + 32 > olim) break;
+        if (lit != 15 && ml != 15) {                          // ends within the window's margin by construction (DEC_WIN + 128 precondition)
+            if (!roomy && acc + 33 > olim) break;
             if (lane == k) { m_tok = q; m_out = acc; }
             acc += int(lit + ml) + 4; q += int(lit) + 3; k++;
             continue;
@@ -137,12 +146,12 @@ __device__ __forceinline__ int decode_batch(const uint8_t* __restrict__ src, uin
         acc += int(lit) + int(ml); q = p2; k++;
     }
     if (k == 0) return 0;
-    {   // plain tokens: lengths from the window, all lanes at once (m_tok < 248)
-        const uint32_t xl = __shfl_sync(B200_FULL, lo, m_tok >> 3), xh = __shfl_sync(B200_FULL, hi, m_tok >> 3);
-        const uint32_t tok = (((m_tok & 4) ? xh : xl) >> ((m_tok & 3) * 8)) & 255u;
-        if (m_lit < 0) { m_lit = int(tok >> 4); m_ml = int(tok & 15u) + 4; m_lsrc = m_tok + 1; }
-        if (lane >= k) { m_lit = 0; m_ml = 0; }
+    if (m_lit < 0) {                                          // plain tokens: lengths from the window, all lanes at once
+        const uint32_t tok = win[m_tok];
+        m_lit = int(tok >> 4); m_ml = int(tok & 15u) + 4; m_lsrc = m_tok + 1;
     }
+    if (lane >= k) { m_lit = 0; m_ml = 0; }
+
     // ---- 2. match offsets, validity
     int off = 1;
     if (lane < k) off = int(in[m_lsrc + m_lit]) | (int(in[m_lsrc + m_lit + 1]) << 8);
@@ -206,6 +215,8 @@ lz4_decompress_safe_kernel(const uint8_t* __restrict__ src_base, const uint64_t*
                            uint8_t* dst_base, const uint64_t* __restrict__ dst_off,
                            const int32_t* __restrict__ dst_cap, int32_t* __restrict__ result, uint32_t n)
 {
+    __shared__ __align__(16) uint8_t s_win[BATCH ? WARPS : 1][DEC_WIN];
+    uint8_t* win = s_win[BATCH ? (threadIdx.x >> 5) : 0];
     const uint32_t b = blockIdx.x * WARPS + (threadIdx.x >> 5);
     if (b >= n) return;
     const int lane = lane_id();
@@ -224,7 +235,7 @@ lz4_decompress_safe_kernel(const uint8_t* __restrict__ src_base, const uint64_t*
         const uint8_t* __restrict__ sl = src + lane;        // per-lane views: sl[i] == src[i + lane]
         uint8_t* dl = dst + lane;
         for (;;) {
-            while (BATCH && fastloop && ip + 384 <= iend && op + 256 <= oend) { if (decode_batch(src, dst, ip, op, iend, oend, lane) == 0) break; }
+            while (BATCH && fastloop && ip + DEC_WIN + 128 <= iend && op + 256 <= oend) { if (decode_batch(src, dst, ip, op, iend, oend, lane, win) == 0) break; }
             // ---- hot loop: the reference's fast-loop common case (lz4.c:2017-2062) — short literal
             // run, short match, far from both ends — decoded with 32-bit bookkeeping and no error
             // exits.  Anything else (length extensions, end-of-block rules, bad offsets) drops to the
@@ -323,6 +334,8 @@ lz4_decompress_fast_kernel(const uint8_t* __restrict__ src_base, const uint64_t*
                            uint8_t* dst_base, const uint64_t* __restrict__ dst_off,
                            const int32_t* __restrict__ dst_len, int32_t* __restrict__ result, uint32_t n)
 {
+    __shared__ __align__(16) uint8_t s_win[BATCH ? WARPS : 1][DEC_WIN];
+    uint8_t* win = s_win[BATCH ? (threadIdx.x >> 5) : 0];
     const uint32_t b = blockIdx.x * WARPS + (threadIdx.x >> 5);
     if (b >= n) return;
     const int lane = lane_id();
@@ -334,7 +347,7 @@ lz4_decompress_fast_kernel(const uint8_t* __restrict__ src_base, const uint64_t*
 
     if (oend < 0) goto done;
     for (;;) {
-        while (BATCH && ip + 384 <= avail && op + 256 <= oend) { if (decode_batch(src, dst, ip, op, avail, oend, lane) == 0) break; }
+        while (BATCH && ip + DEC_WIN + 128 <= avail && op + 256 <= oend) { if (decode_batch(src, dst, ip, op, avail, oend, lane, win) == 0) break; }
         {   // hot loop: short literal run + short match, away from both ends (rules below cannot fire)
             const uint8_t* __restrict__ sl = src + lane;
             uint8_t* dl = dst + lane;
