@@ -283,7 +283,8 @@ static int hash_host_batch(int bits, const uint8_t* base, const uint64_t* off, c
         g_launches.fetch_add(1, std::memory_order_relaxed);
         if (bits == 32) CK((span / nb >= 32768 ? launch_xxh32_long : launch_xxh32)(            // few long streams: one warp each
                                s.d_src, s.d_soff(), s.d_slen(), (uint32_t)seed, (uint32_t*)s.d_doff(), nb, s.st));
-        else            CK(launch_xxh64(s.d_src, s.d_soff(), s.d_slen(), seed, (uint64_t*)s.d_doff(), nb, s.st));
+        else            CK((span / nb >= 32768 ? launch_xxh64_long : launch_xxh64)(
+                               s.d_src, s.d_soff(), s.d_slen(), seed, (uint64_t*)s.d_doff(), nb, s.st));
         CK(cudaMemcpyAsync(s.h_doff(), s.d_doff(), nb * sizeof(W), cudaMemcpyDeviceToHost, s.st));
         CK(cudaEventRecord(s.done, s.st));
         s.busy = true; s.i0 = i0; s.i1 = i1;

@@ -37,6 +37,9 @@ cudaError_t launch_xxh32_stream(Xxh32State* st, int op, uint32_t seed, const uin
 cudaError_t launch_xxh64_stream(Xxh64State* st, int op, uint64_t seed, const uint8_t* data, size_t len, cudaStream_t s);
 enum { XXH_OP_RESET = 0, XXH_OP_UPDATE = 1, XXH_OP_DIGEST = 2 };
 
+cudaError_t launch_xxh64_long(const uint8_t* base, const uint64_t* off, const int32_t* len, uint64_t seed,
+                              uint64_t* out, size_t n, cudaStream_t st);
+
 // prefix-sum compaction of variable-length outputs (compact_host path)
 cudaError_t launch_compact(const uint8_t* slots, const uint64_t* slot_off, const int32_t* lens,
                            uint8_t* out, uint64_t* out_off, uint64_t* total, size_t n, cudaStream_t st);

@@ -302,6 +302,98 @@ cudaError_t launch_xxh32_long(const uint8_t* base, const uint64_t* off, const in
     return cudaGetLastError();
 }
 
+// ---- the same for XXH64: stripes of 32 bytes, rows of 256 bytes (one 64-bit word per lane), chain = lane & 3.
+__device__ __forceinline__ uint64_t xxh64_chain_init(uint64_t seed, int lane)
+{
+    const int c = lane & 3;
+    return c == 0 ? seed + P64_1 + P64_2 : c == 1 ? seed + P64_2 : c == 2 ? seed : seed - P64_1;
+}
+
+__device__ __forceinline__ uint64_t xxh64_warp_rows(uint64_t v, const uint8_t* __restrict__ p, size_t rows, int lane)
+{
+    constexpr int R = 4;
+    const uintptr_t sa = reinterpret_cast<uintptr_t>(p);
+    const uint32_t* __restrict__ W = reinterpret_cast<const uint32_t*>(sa & ~uintptr_t(3));
+    const uint32_t sh = (uint32_t(sa) & 3u) * 8u;
+    const int c = lane & 3;
+    auto ldrow = [&](size_t r) -> uint2 {
+        const size_t i = (r * 32 + lane) * 2;
+        const uint32_t a = W[i], b = W[i + 1];
+        if (!sh) return make_uint2(a, b);
+        return make_uint2(__funnelshift_r(a, b, sh), __funnelshift_r(b, W[i + 2], sh));
+    };
+    auto feed = [&](uint2 x) {
+        #pragma unroll
+        for (int st = 0; st < 8; st++) {
+            const uint32_t lo = __shfl_sync(B200_FULL, x.x, 4 * st + c), hi = __shfl_sync(B200_FULL, x.y, 4 * st + c);
+            v = round64(v, uint64_t(lo) | (uint64_t(hi) << 32));
+        }
+    };
+    uint2 cur[R], nxt[R];
+    const size_t groups = rows / R;
+    if (groups) {
+        #pragma unroll
+        for (int r = 0; r < R; r++) cur[r] = ldrow(r);
+    }
+    for (size_t g = 0; g < groups; g++) {
+        if (g + 1 < groups) {
+            #pragma unroll
+            for (int r = 0; r < R; r++) nxt[r] = ldrow((g + 1) * R + r);
+        }
+        #pragma unroll
+        for (int r = 0; r < R; r++) feed(cur[r]);
+        #pragma unroll
+        for (int r = 0; r < R; r++) cur[r] = nxt[r];
+    }
+    for (size_t r = groups * R; r < rows; r++) feed(ldrow(r));
+    return v;
+}
+
+__device__ __forceinline__ uint64_t xxh64_warp_stripes(uint64_t v, const uint8_t* __restrict__ p, size_t stripes, int lane)
+{
+    const size_t rows = stripes >> 3;
+    v = xxh64_warp_rows(v, p, rows, lane);
+    for (size_t t = rows << 3; t < stripes; t++) v = round64(v, load_u64_unaligned(p + 32 * t + 8 * (lane & 3)));
+    return v;
+}
+
+__device__ __forceinline__ uint64_t shfl_u64(uint64_t x, int src)
+{
+    return uint64_t(__shfl_sync(B200_FULL, uint32_t(x), src)) | (uint64_t(__shfl_sync(B200_FULL, uint32_t(x >> 32), src)) << 32);
+}
+
+__device__ __forceinline__ uint64_t xxh64_chain_merge(uint64_t v)      // xxhash.c:792-802
+{
+    const uint64_t v1 = shfl_u64(v, 0), v2 = shfl_u64(v, 1), v3 = shfl_u64(v, 2), v4 = shfl_u64(v, 3);
+    uint64_t h = rotl64(v1, 1) + rotl64(v2, 7) + rotl64(v3, 12) + rotl64(v4, 18);
+    h = merge64(h, v1); h = merge64(h, v2); h = merge64(h, v3); h = merge64(h, v4);
+    return h;
+}
+
+__global__ void __launch_bounds__(32)
+xxh64_long_kernel(const uint8_t* __restrict__ base, const uint64_t* __restrict__ off, const int32_t* __restrict__ len,
+                  uint64_t seed, uint64_t* __restrict__ out, uint32_t n)
+{
+    const uint32_t i = blockIdx.x;
+    if (i >= n) return;
+    const int lane = lane_id();
+    const uint8_t* __restrict__ p = base + off[i];
+    const uint32_t L = (uint32_t)max(len[i], 0);
+    const size_t stripes = L >> 5;
+    uint64_t h;
+    if (L >= 32u) h = xxh64_chain_merge(xxh64_warp_stripes(xxh64_chain_init(seed, lane), p, stripes, lane));
+    else h = seed + P64_5;
+    if (lane == 0) out[i] = finish64(h + uint64_t(L), p + 32 * stripes, L & 31u);
+}
+
+cudaError_t launch_xxh64_long(const uint8_t* base, const uint64_t* off, const int32_t* len, uint64_t seed,
+                              uint64_t* out, size_t n, cudaStream_t st)
+{
+    if (n == 0) return cudaSuccess;
+    xxh64_long_kernel<<<(unsigned)n, 32, 0, st>>>(base, off, len, seed, out, (uint32_t)n);
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------ streaming state (device-resident)
 // One lane walks the XXH32_update / XXH64_update state machine (xxhash.c:515-546, 971-1002); the
 // serial dependency makes more lanes pointless.  reset / digest are the same kernel with op codes.
@@ -355,28 +447,41 @@ __global__ void xxh32_stream_kernel(Xxh32State* s, int op, uint32_t seed, const 
 
 __global__ void xxh64_stream_kernel(Xxh64State* s, int op, uint64_t seed, const uint8_t* __restrict__ p, size_t len)
 {
-    if (threadIdx.x != 0) return;
+    const int lane = lane_id();
     if (op == XXH_OP_RESET) {
+        if (lane) return;
         s->total = 0; s->memsize = 0; s->seed = seed;
         s->v[0] = seed + P64_1 + P64_2; s->v[1] = seed + P64_2; s->v[2] = seed; s->v[3] = seed - P64_1;
         return;
     }
-    if (op == XXH_OP_UPDATE) {
-        const uint8_t* end = p + len;
-        s->total += len;
-        if (s->memsize + len < 32) { for (size_t i = 0; i < len; i++) s->mem[s->memsize + i] = p[i]; s->memsize += (uint32_t)len; return; }
-        Acc<64> a; a.v1 = s->v[0]; a.v2 = s->v[1]; a.v3 = s->v[2]; a.v4 = s->v[3];
-        if (s->memsize) {
-            const uint32_t fill = 32 - s->memsize;
-            for (uint32_t i = 0; i < fill; i++) s->mem[s->memsize + i] = p[i];
-            a.stripe_g(s->mem); p += fill; s->memsize = 0;
+    if (op == XXH_OP_UPDATE) {                               // XXH64_update (xxhash.c:971-1002), stripe loop by the warp
+        const uint32_t memsize = s->memsize;
+        const uint64_t total = s->total;
+        uint64_t v = s->v[lane & 3];
+        __syncwarp();
+        if (memsize + len < 32) {
+            if (lane == 0) { for (size_t i = 0; i < len; i++) s->mem[memsize + i] = p[i]; s->memsize = memsize + (uint32_t)len; s->total = total + len; }
+            return;
         }
-        while (p + 32 <= end) { a.stripe_g(p); p += 32; }
-        s->v[0] = a.v1; s->v[1] = a.v2; s->v[2] = a.v3; s->v[3] = a.v4;
-        uint32_t r = 0; while (p < end) s->mem[r++] = *p++;
-        s->memsize = r;
+        if (memsize) {
+            const uint32_t fill = 32 - memsize;
+            if (lane == 0) for (uint32_t i = 0; i < fill; i++) s->mem[memsize + i] = p[i];
+            __syncwarp();
+            v = round64(v, load_u64_unaligned(s->mem + 8 * (lane & 3)));
+            p += fill; len -= fill;
+            __syncwarp();
+        }
+        const size_t stripes = len >> 5;
+        v = xxh64_warp_stripes(v, p, stripes, lane);
+        if (lane < 4) s->v[lane] = v;
+        if (lane == 0) {
+            const uint32_t r = (uint32_t)(len & 31);
+            for (uint32_t i = 0; i < r; i++) s->mem[i] = p[32 * stripes + i];
+            s->memsize = r; s->total = total + (memsize ? 32 - memsize : 0) + len;
+        }
         return;
     }
+    if (lane) return;
     {
         uint64_t h;
         if (s->total >= 32) {

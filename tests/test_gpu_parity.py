@@ -304,7 +304,7 @@ def test_xxhash_uniform_4k(b200, checker):
         assert int(h32[k]) == checker.xxh32(blk, 0x9747B28C)
 
 
-def test_xxhash32_long_streams(b200, checker):
+def test_xxhash_long_streams(b200, checker):
     """a few long buffers take the one-warp-per-stream kernel: every alignment phase, every tail length"""
     rng = random.Random(21)
     blob = np.frombuffer(rng.randbytes(6 << 20), dtype=np.uint8).copy()
@@ -317,15 +317,18 @@ def test_xxhash32_long_streams(b200, checker):
     off = np.array(offs, dtype=np.uint64); ln = np.array(lens, dtype=np.int32)
     for seed in (0, 0x9747B28C):
         h = b200.batch.xxh32_batch_host(blob, off, ln, seed)
+        h64 = b200.batch.xxh64_batch_host(blob, off, ln, seed)
         for k in range(len(offs)):
             assert int(h[k]) == checker.xxh32(blob[offs[k]:offs[k] + lens[k]], seed), (k, offs[k], lens[k])
-    # the streaming state takes the same warp loop for large updates
+            assert int(h64[k]) == checker.xxh64(blob[offs[k]:offs[k] + lens[k]], seed), (k, offs[k], lens[k])
+    # the streaming states take the same warp loops for large updates
     f = b200.XXHashFactory.b200Instance()
     data = blob[3:3 + (1 << 20) + 5].tobytes()
-    h = f.newStreamingHash32(7)
-    h.update(data, 0, 5); h.update(data, 5, 70001); h.update(data, 70006, len(data) - 70006)
-    assert h.getValue() == checker.xxh32(data, 7)
-    h.close()
+    for mk, ref in ((f.newStreamingHash32, checker.xxh32), (f.newStreamingHash64, checker.xxh64)):
+        h = mk(7)
+        h.update(data, 0, 5); h.update(data, 5, 70001); h.update(data, 70006, len(data) - 70006)
+        assert h.getValue() == ref(data, 7)
+        h.close()
 
 
 def test_xxhash_streaming(b200, checker):
