@@ -582,6 +582,7 @@ lz4_compress_fast3_kernel(const uint8_t* __restrict__ src_base, const uint64_t* 
     int ip = 0, anchor = 0;
     auto walk = [&](int c) {
         const int cp0 = 128 * c - int(ph), buf = c % NB;
+        const bool inner = cp0 >= 4 && cp0 + 128 + 32 <= n;  // every measurement window of this chunk lies inside the block
         int k = 0;
         const int r0 = max(ip - cp0, 0);
         int nh = 0;
@@ -610,10 +611,17 @@ lz4_compress_fast3_kernel(const uint8_t* __restrict__ src_base, const uint64_t* 
                 const uint32_t am = uint32_t(ms + 4) + ph, ac = uint32_t(mc + 4) + ph;     // +4: (pos - 4) never negative in the view
                 const uint32_t lastw = (uint32_t(n - 1) + ph) >> 2;
                 uint32_t wm[7], wc[7];
-                #pragma unroll
-                for (int t = 0; t < 7; t++) {
-                    wm[t] = wsrc[min((am >> 2) - 2 + t, lastw)];
-                    wc[t] = mc >= 4 ? wsrc[min((ac >> 2) - 2 + t, lastw)] : 0u;
+                if (inner) {                                     // the 28 bytes behind the hit are inside the block: no clamping
+                    const uint32_t* pm = wsrc + (am >> 2) - 2;
+                    const uint32_t* pc = wsrc + (mc >= 4 ? (ac >> 2) - 2 : 0u);
+                    #pragma unroll
+                    for (int t = 0; t < 7; t++) { wm[t] = pm[t]; wc[t] = pc[t]; }
+                } else {
+                    #pragma unroll
+                    for (int t = 0; t < 7; t++) {
+                        wm[t] = wsrc[min((am >> 2) - 2 + t, lastw)];
+                        wc[t] = mc >= 4 ? wsrc[min((ac >> 2) - 2 + t, lastw)] : 0u;
+                    }
                 }
                 const uint32_t sm = (am & 3u) * 8u, sc = (ac & 3u) * 8u;
                 if (mc >= 4) {
