@@ -405,6 +405,9 @@ static cudaError_t launch_v2(const BatchArgs& a, cudaStream_t st)
 #ifndef B200_V3_MINB
 #define B200_V3_MINB 12
 #endif
+#ifndef B200_V3_FENCE
+#define B200_V3_FENCE 0
+#endif
 #ifndef B200_V3_MINB12
 #define B200_V3_MINB12 16
 #endif
@@ -412,6 +415,9 @@ static cudaError_t launch_v2(const BatchArgs& a, cudaStream_t st)
 #define B200_BAR_CASE(OP, N) case N: asm volatile(OP " " #N ", 64;" ::: "memory"); break;
 __device__ __forceinline__ void bar_arrive(int id)
 {
+#if B200_V3_FENCE
+    __threadfence_block();                               // order this warp's shared-memory writes before the arrival
+#endif
     switch (id) { B200_BAR_CASE("bar.arrive", 1) B200_BAR_CASE("bar.arrive", 2) B200_BAR_CASE("bar.arrive", 3)
                   B200_BAR_CASE("bar.arrive", 4) B200_BAR_CASE("bar.arrive", 5) B200_BAR_CASE("bar.arrive", 6)
                   B200_BAR_CASE("bar.arrive", 7) default: asm volatile("bar.arrive 8, 64;" ::: "memory"); }

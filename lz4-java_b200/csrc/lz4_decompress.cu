@@ -113,7 +113,6 @@ __device__ __forceinline__ int decode_batch(const uint8_t* __restrict__ src, uin
     auto wbyte = [&](int q) -> uint32_t { return q < DEC_WIN ? win[q] : in[q]; };
     const int ilim = iend - ip - 64;                         // a sequence must end at or before in[ilim]
     const int olim = oend - op - 128;                        // ... and its output at or before dst[op + olim]
-    const bool roomy = olim >= 32 * 33;                      // 32 plain sequences (<= 33 bytes each) cannot reach olim
 
     // ---- 1. token chain.  Lane k keeps where sequence k's token is and where its output starts; the common
     // token (no length extension) is decoded after the walk, by all lanes at once.
@@ -123,7 +122,7 @@ __device__ __forceinline__ int decode_batch(const uint8_t* __restrict__ src, uin
         const uint32_t tok = win[q];
         uint32_t lit = tok >> 4, ml = tok & 15u;
         if (lit != 15 && ml != 15) {                          // ends within the window's margin by construction (DEC_WIN + 128 precondition)
-            if (!roomy && acc + 33 > olim) break;
+            if (acc + 33 > olim) break;                      // (checked per sequence: earlier long sequences of the batch count too)
             if (lane == k) { m_tok = q; m_out = acc; }
             acc += int(lit + ml) + 4; q += int(lit) + 3; k++;
             continue;

@@ -168,6 +168,48 @@ def test_decompress_dependency_patterns(b200, checker, decoder):
             assert (dst[end:end + 13] == 0x55).all(), (decoder, fast, k)
 
 
+def test_decompress_long_sequence_then_short_ones_near_the_end(b200, checker, decoder):
+    """Regression: a long match followed by many short sequences close to the end of the block — the batched decoder
+    must count the long one against the output margin too (it once skipped the per-sequence check when the margin
+    looked roomy at the start of a batch, accepted sequences inside the margin and walked past the end of the
+    stream).  The fast decoder is given far more readable input than the stream holds, and what follows the stream
+    looks like more LZ4 sequences (another block's stream) — what a caller with bound-sized slots that were used
+    before hands over."""
+    rng = random.Random(8080)
+    items = []
+    for trial in range(48):
+        hist = bytes(rng.randrange(256) for _ in range(3000))
+        parts = [hist]
+
+        def short():                                                             # 1-6 literals + 5-12 byte match
+            parts.append(bytes(rng.randrange(256) for _ in range(rng.randrange(1, 7))))
+            a = rng.randrange(0, 2900); parts.append(hist[a:a + rng.randrange(5, 13)])
+        for _ in range(rng.randrange(40, 90)): short()
+        a = rng.randrange(0, 500)
+        parts.append(bytes(rng.randrange(256) for _ in range(2))); parts.append(hist[a:a + rng.randrange(900, 2400)])   # the long one
+        for _ in range(rng.randrange(30, 90)): short()
+        parts.append(bytes(rng.randrange(256) for _ in range(rng.randrange(5, 40))))
+        items.append(b"".join(parts))
+    items.append(bytes(70000))                                                   # 640 bytes of input = most of the block
+    items.append(bytes([7]) * 40000 + bytes(rng.randrange(256) for _ in range(300)) + bytes([9]) * 3000)
+    comp = [checker.compress(d) for d in items]
+    lens = np.array([len(d) for d in items], dtype=np.int32)
+    src, soff, slen = corpus.pack(comp)
+    doff, dcap, total = _slots([len(d) for d in items], align=64)
+    dst = np.full(total + 4096, 0x55, dtype=np.uint8)
+    res = b200.batch.decompress_safe_batch_host(src, soff, slen, dst, doff, dcap)
+    for k, d in enumerate(items):
+        assert res[k] == len(d) and dst[int(doff[k]):int(doff[k]) + len(d)].tobytes() == d, (decoder, "safe", k)
+        assert (dst[int(doff[k]) + len(d):int(doff[k]) + len(d) + 16] == 0x55).all(), (decoder, "safe", k)
+    padded = [c + comp[(k + 1) % len(comp)][9:3000] + bytes(64) for k, c in enumerate(comp)]
+    src, soff, slen = corpus.pack(padded)
+    dst = np.full(total + 4096, 0x55, dtype=np.uint8)
+    res = b200.batch.decompress_fast_batch_host(src, soff, slen, dst, doff, lens)
+    for k, d in enumerate(items):
+        assert res[k] == len(comp[k]) and dst[int(doff[k]):int(doff[k]) + len(d)].tobytes() == d, (decoder, "fast", k)
+        assert (dst[int(doff[k]) + len(d):int(doff[k]) + len(d) + 16] == 0x55).all(), (decoder, "fast", k)
+
+
 def _knob(b200, name, value):
     import ctypes
     ctypes.c_int.in_dll(b200._native.lib(), name).value = value
@@ -517,3 +559,37 @@ def test_frame_writer_and_lz4java_containers(b200, port):
         b200.decompress_lz4block(bytes(bad), 70000)
     with pytest.raises(EOFError):
         b200.decompress_lz4block(good[:100], 70000)
+
+
+def test_decompress_fast_does_not_walk_past_the_stream(b200, checker, decoder):
+    """The same regression, aimed: blocks ending  …long match, a few short sequences, 5-14 last literals, built so that
+    the old batched walk (modelled on the CPU while writing this test) takes the final literal-only token for a full
+    sequence in 6 of the 96 blocks; what follows each stream starts with the bytes 01 00 — a valid-looking offset —
+    and continues with another block's sequences.  (Last in the file: added after the round's GPU budget was spent, so
+    its first GPU run is the round-end one.)"""
+    rng = random.Random(8080)
+    items = []
+    for trial in range(96):
+        hist = bytes(rng.randrange(256) for _ in range(3000))
+        parts = [hist]
+
+        def short():
+            parts.append(bytes(rng.randrange(256) for _ in range(rng.randrange(1, 7))))
+            a = rng.randrange(0, 2900); parts.append(hist[a:a + rng.randrange(5, 13)])
+        for _ in range(rng.randrange(40, 90)): short()
+        a = rng.randrange(0, 500)
+        parts.append(bytes(rng.randrange(256) for _ in range(2))); parts.append(hist[a:a + rng.randrange(1100, 1700)])
+        for _ in range(rng.randrange(3, 26)): short()
+        parts.append(bytes(rng.randrange(256) for _ in range(rng.randrange(5, 15))))
+        items.append(b"".join(parts))
+    comp = [checker.compress(d) for d in items]
+    lens = np.array([len(d) for d in items], dtype=np.int32)
+    padded = [c + b"\x01\x00" + comp[(k + 1) % len(comp)][9:3000] + bytes(64) for k, c in enumerate(comp)]
+    src, soff, slen = corpus.pack(padded)
+    doff, dcap, total = _slots([len(d) for d in items], align=64)
+    dst = np.full(total + 4096, 0x55, dtype=np.uint8)
+    res = b200.batch.decompress_fast_batch_host(src, soff, slen, dst, doff, lens)
+    for k, d in enumerate(items):
+        assert res[k] == len(comp[k]), (decoder, k, int(res[k]), len(comp[k]))
+        assert dst[int(doff[k]):int(doff[k]) + len(d)].tobytes() == d, (decoder, k)
+        assert (dst[int(doff[k]) + len(d):int(doff[k]) + len(d) + 16] == 0x55).all(), (decoder, k)
