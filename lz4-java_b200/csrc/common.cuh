@@ -5,7 +5,11 @@
 // blocks are called CTAs.
 #pragma once
 #include <cstdint>
+#ifdef B200_HOST_SIM            // tests/simt: the same kernel source run by a CPU SIMT emulator (test infrastructure only)
+#include "simt.h"
+#else
 #include <cuda_runtime.h>
+#endif
 
 #define B200_FULL 0xFFFFFFFFu
 
@@ -32,9 +36,13 @@ __device__ __forceinline__ uint32_t load_u32_unaligned(const uint8_t* p)
 // the scattered look-back lines from evicting the sequential input stream.
 __device__ __forceinline__ uint8_t load_u8_l2(const uint8_t* p)
 {
+#ifdef B200_HOST_SIM
+    return *p;
+#else
     uint32_t v;
     asm volatile("ld.global.cg.u8 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return uint8_t(v);
+#endif
 }
 
 // Cooperative copy of n bytes between NON-overlapping ranges (or ranges whose distance is at

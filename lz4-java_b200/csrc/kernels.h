@@ -2,7 +2,11 @@
 #pragma once
 #include <cstddef>
 #include <cstdint>
+#ifdef B200_HOST_SIM
+#include "simt.h"
+#else
 #include <cuda_runtime.h>
+#endif
 
 namespace b200 {
 

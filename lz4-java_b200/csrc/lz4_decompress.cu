@@ -405,6 +405,7 @@ done:
     if (lane == 0) result[b] = ret;
 }
 
+#ifndef B200_HOST_SIM          // launchers: CUDA only (tests/simt drives the kernels directly)
 static constexpr int DEC_WARPS = 4;
 
 } // namespace b200
@@ -437,5 +438,7 @@ cudaError_t launch_decompress_fast(const BatchArgs& a, cudaStream_t st)
             a.src_base, a.src_off, a.src_len, a.dst_base, a.dst_off, a.dst_cap, a.result, (uint32_t)a.n);
     return cudaGetLastError();
 }
+
+#endif
 
 } // namespace b200

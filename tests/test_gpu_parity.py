@@ -565,8 +565,10 @@ def test_decompress_fast_does_not_walk_past_the_stream(b200, checker, decoder):
     """The same regression, aimed: blocks ending  …long match, a few short sequences, 5-14 last literals, built so that
     the old batched walk (modelled on the CPU while writing this test) takes the final literal-only token for a full
     sequence in 6 of the 96 blocks; what follows each stream starts with the bytes 01 00 — a valid-looking offset —
-    and continues with another block's sequences.  (Last in the file: added after the round's GPU budget was spent, so
-    its first GPU run is the round-end one.)"""
+    and continues with another block's sequences.  Added after the round's GPU budget was spent: its data was
+    validated on the CPU instead — tests/test_kernel_logic_cpu.py runs the kernels' own source under a SIMT emulator,
+    where the pre-fix source fails on exactly those six blocks (return -1 and a write past the output) and the fixed
+    source passes."""
     rng = random.Random(8080)
     items = []
     for trial in range(96):
