@@ -13,6 +13,17 @@
 
 #define B200_FULL 0xFFFFFFFFu
 
+// The few things that are PTX or CUDA-only syntax go through these, so that tests/simt can run the same source.
+#ifdef B200_HOST_SIM
+#define B200_DYN_SMEM(name, al) uint8_t* name = simt::dyn_smem()
+#define B200_PREFETCH_L2(ptr) ((void)(ptr))
+#define B200_PREFETCH_L1(ptr) ((void)(ptr))
+#else
+#define B200_DYN_SMEM(name, al) extern __shared__ __align__(al) uint8_t name[]
+#define B200_PREFETCH_L2(ptr) asm volatile("prefetch.global.L2 [%0];" :: "l"(__cvta_generic_to_global(ptr)))
+#define B200_PREFETCH_L1(ptr) asm volatile("prefetch.global.L1 [%0];" :: "l"(__cvta_generic_to_global(ptr)))
+#endif
+
 namespace b200 {
 
 __device__ __forceinline__ int lane_id() { return threadIdx.x & 31; }

@@ -50,7 +50,7 @@ __device__ __forceinline__ int compress_block(const In in, const uint8_t* __rest
         if (std::is_same<In, InGlobal>::value) {
             if (pf < ip + 2048) {      // keep ~4 KiB of the forward stream on its way to L2
                 const int qq = pf + lane * 128;
-                if (qq < n) asm volatile("prefetch.global.L2 [%0];" :: "l"(__cvta_generic_to_global(gsrc + qq)));
+                if (qq < n) B200_PREFETCH_L2(gsrc + qq);
                 pf += 4096;
             }
         }
@@ -58,7 +58,7 @@ __device__ __forceinline__ int compress_block(const In in, const uint8_t* __rest
         uint32_t litv = 0;
         if (have && lane < q.ms - q.anchor && q.ms - q.anchor <= 32) litv = in.ld1(q.anchor + lane);
         if (std::is_same<In, InGlobal>::value && lane == 0 && ip + 160 < n)     // next line of the forward stream -> L1
-            asm volatile("prefetch.global.L1 [%0];" :: "l"(__cvta_generic_to_global(gsrc + ip + 128)));
+            B200_PREFETCH_L1(gsrc + ip + 128);
         const int p = ip + lane;
         const bool valid = p <= mflimit;
         const int pp = min(p, mflimit);
@@ -129,7 +129,7 @@ lz4_compress_fast_kernel(const uint8_t* __restrict__ src_base, const uint64_t* _
                          const int32_t* __restrict__ dst_cap, int32_t* __restrict__ result, uint32_t nblocks)
 {
     using Entry = typename std::conditional<U16, uint16_t, uint32_t>::type;
-    extern __shared__ __align__(128) uint8_t smem_raw[];
+    B200_DYN_SMEM(smem_raw, 128);
     Entry* table = reinterpret_cast<Entry*>(smem_raw);
     constexpr int TABLE_BYTES = int(sizeof(Entry) << HASH_LOG);
 
@@ -153,8 +153,13 @@ lz4_compress_fast_kernel(const uint8_t* __restrict__ src_base, const uint64_t* _
         // whole block -> shared memory: one TMA bulk copy (16-byte aligned part) + a lane-copied tail
         uint8_t* stage = smem_raw + TABLE_BYTES + 16;
         const uint32_t bar = (uint32_t)__cvta_generic_to_shared(smem_raw + TABLE_BYTES);
+#ifdef B200_HOST_SIM
+        const bool aligned = false;                          // no TMA in the emulator: the lane copy below stages everything
+#else
         const bool aligned = (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+#endif
         const int bulk = aligned ? (n & ~15) : 0;
+#ifndef B200_HOST_SIM
         if (lane == 0 && bulk) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bar) : "memory");
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -162,8 +167,10 @@ lz4_compress_fast_kernel(const uint8_t* __restrict__ src_base, const uint64_t* _
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                          :: "r"((uint32_t)__cvta_generic_to_shared(stage)), "l"(src), "r"(bulk), "r"(bar) : "memory");
         }
+#endif
         for (int i = bulk + lane; i < n; i += 32) stage[i] = src[i];
         __syncwarp();
+#ifndef B200_HOST_SIM
         if (bulk) {
             uint32_t ok;
             do {
@@ -171,6 +178,7 @@ lz4_compress_fast_kernel(const uint8_t* __restrict__ src_base, const uint64_t* _
                              : "=r"(ok) : "r"(bar) : "memory");
             } while (!ok);
         }
+#endif
         __syncwarp();
         ret = compress_block<HASH_LOG, U16>(InShared{stage}, src, n, dst, cap, table, lane);
     } else {
@@ -211,7 +219,7 @@ lz4_compress_fast2_kernel(const uint8_t* __restrict__ src_base, const uint64_t* 
 {
     using Entry = typename std::conditional<U16, uint16_t, uint32_t>::type;
     constexpr int TABLE_BYTES = int(sizeof(Entry) << HASH_LOG);
-    extern __shared__ __align__(128) uint8_t smem_raw[];
+    B200_DYN_SMEM(smem_raw, 128);
     Entry* table = reinterpret_cast<Entry*>(smem_raw);
     uint16_t* s_dist = reinterpret_cast<uint16_t*>(smem_raw + TABLE_BYTES);        // [128] match distance, 0 = no match at this position
 
@@ -263,7 +271,7 @@ lz4_compress_fast2_kernel(const uint8_t* __restrict__ src_base, const uint64_t* 
             const int cp0 = 128 * c - int(ph);                     // position of the chunk's first byte
             if (lane < 2) {                                        // two chunks ahead -> L2
                 const int pfq = cp0 + 512 + lane * 128;
-                if (pfq < n) asm volatile("prefetch.global.L2 [%0];" :: "l"(__cvta_generic_to_global(src + pfq)));
+                if (pfq < n) B200_PREFETCH_L2(src + pfq);
             }
             // ---------------- phase AB
             const int p0 = cp0 + 4 * lane;
@@ -367,6 +375,7 @@ done:
     if (lane == 0) result[b] = ret;
 }
 
+#ifndef B200_HOST_SIM
 template <int HASH_LOG, bool U16>
 static cudaError_t launch_v2(const BatchArgs& a, cudaStream_t st)
 {
@@ -379,6 +388,7 @@ static cudaError_t launch_v2(const BatchArgs& a, cudaStream_t st)
                                        a.result, (uint32_t)a.n);
     return cudaGetLastError();
 }
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // Warp-specialised pipeline (algo 3): the decoupled parser above, split across producer/consumer warps of
@@ -411,6 +421,10 @@ static cudaError_t launch_v2(const BatchArgs& a, cudaStream_t st)
 #ifndef B200_V3_MINB12
 #define B200_V3_MINB12 16
 #endif
+#ifdef B200_HOST_SIM
+__device__ __forceinline__ void bar_arrive(int id) { simt::bar_arrive(id, 64); }
+__device__ __forceinline__ void bar_wait(int id) { simt::bar_sync(id, 64); }
+#else
 // (Immediate barrier ids, so ptxas reserves only the barriers in use and not all 16.)
 #define B200_BAR_CASE(OP, N) case N: asm volatile(OP " " #N ", 64;" ::: "memory"); break;
 __device__ __forceinline__ void bar_arrive(int id)
@@ -429,6 +443,8 @@ __device__ __forceinline__ void bar_wait(int id)
                   B200_BAR_CASE("bar.sync", 7) default: asm volatile("bar.sync 8, 64;" ::: "memory"); }
 }
 
+#endif
+
 template <int HASH_LOG, bool SPARSE>
 __global__ void __launch_bounds__(32 * B200_V3_WARPS, HASH_LOG == 13 ? B200_V3_MINB : B200_V3_MINB12)
 lz4_compress_fast3_kernel(const uint8_t* __restrict__ src_base, const uint64_t* __restrict__ src_off,
@@ -441,7 +457,7 @@ lz4_compress_fast3_kernel(const uint8_t* __restrict__ src_base, const uint64_t* 
     constexpr int BAR_FULL = 1, BAR_WALKED = 1 + NB, BAR_DFREE = 1 + 2 * NB, BAR_RFREE = 1 + 3 * NB;
     static_assert(NW == 2 || 4 * NB <= 8, "named barrier ids 1..8");
     constexpr int TABLE_BYTES = 2 << HASH_LOG;
-    extern __shared__ __align__(128) uint8_t smem_raw[];
+    B200_DYN_SMEM(smem_raw, 128);
     uint16_t* table = reinterpret_cast<uint16_t*>(smem_raw);
     uint16_t* s_dist = reinterpret_cast<uint16_t*>(smem_raw + TABLE_BYTES);                 // [NB][128] distance per position, 0 = no match
     uint2* s_rec = reinterpret_cast<uint2*>(smem_raw + TABLE_BYTES + NB * 256);             // [NB][32]  x = start | distance << 16, y = length
@@ -476,7 +492,7 @@ lz4_compress_fast3_kernel(const uint8_t* __restrict__ src_base, const uint64_t* 
         const int cp0 = 128 * c - int(ph), buf = c % NB;
         if (lane < 2) {
             const int pfq = cp0 + 512 + lane * 128;
-            if (pfq < n) asm volatile("prefetch.global.L2 [%0];" :: "l"(__cvta_generic_to_global(src + pfq)));
+            if (pfq < n) B200_PREFETCH_L2(src + pfq);
         }
         const int p0 = cp0 + 4 * lane;
         uint32_t w0 = 0, w1 = 0;
@@ -727,6 +743,7 @@ lz4_compress_fast3_kernel(const uint8_t* __restrict__ src_base, const uint64_t* 
     }
 }
 
+#ifndef B200_HOST_SIM
 template <int HASH_LOG, bool SPARSE>
 static cudaError_t launch_v3(const BatchArgs& a, cudaStream_t st)
 {
@@ -739,6 +756,7 @@ static cudaError_t launch_v3(const BatchArgs& a, cudaStream_t st)
                                                         a.result, (uint32_t)a.n);
     return cudaGetLastError();
 }
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // Three-kernel pipeline (algo 4): the three phases of the decoupled parser as three launches over a
@@ -763,7 +781,7 @@ lz4c4_lookup_kernel(const uint8_t* __restrict__ src_base, const uint64_t* __rest
                     const int32_t* __restrict__ src_len, uint32_t first, uint32_t nsb,
                     uint16_t* __restrict__ g_dist, uint32_t* __restrict__ g_mask)
 {
-    extern __shared__ __align__(128) uint8_t smem_raw[];
+    B200_DYN_SMEM(smem_raw, 128);
     uint16_t* table = reinterpret_cast<uint16_t*>(smem_raw);
     const uint32_t sb = blockIdx.x;
     if (sb >= nsb) return;
@@ -783,7 +801,7 @@ lz4c4_lookup_kernel(const uint8_t* __restrict__ src_base, const uint64_t* __rest
         const int cp0 = 128 * c - int(ph);
         if (lane < 2) {
             const int pfq = cp0 + 512 + lane * 128;
-            if (pfq < n) asm volatile("prefetch.global.L2 [%0];" :: "l"(__cvta_generic_to_global(src + pfq)));
+            if (pfq < n) B200_PREFETCH_L2(src + pfq);
         }
         const int p0 = cp0 + 4 * lane;
         uint32_t w0 = 0, w1 = 0;
@@ -984,6 +1002,7 @@ done:
 }
 
 // scratch arena: one per (calling thread, stream) so concurrent pipelines never share it
+#ifndef B200_HOST_SIM          // host side: arenas, launchers, knobs
 struct K4Arena { cudaStream_t st; int device; uint32_t blocks; uint16_t* dist; uint32_t* mask; uint2* rec; int32_t* cnt; };
 static thread_local K4Arena t_arenas[8];
 static thread_local int t_narenas = 0;
@@ -1083,5 +1102,7 @@ cudaError_t launch_compress_fast(const BatchArgs& a, int max_src_len, cudaStream
     }
     return launch_variant<12, false, false>(a, st);   // 4096 x u32 = 16 KiB, the reference's byU32 table (lz4.c:1356)
 }
+
+#endif
 
 } // namespace b200

@@ -24,10 +24,15 @@ struct InShared {
     const uint8_t* p;     // generic pointer into the CTA's shared memory
     __device__ __forceinline__ uint32_t ld1(int i) const { return p[i]; }
     __device__ __forceinline__ uint32_t ld4(int i) const {
+#ifdef B200_HOST_SIM
+        return load_u32_unaligned(p + i);
+#endif
         const uint32_t a = (uint32_t)__cvta_generic_to_shared(p) + (uint32_t)i;
         uint32_t lo, hi;
+#ifndef B200_HOST_SIM
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(lo) : "r"(a & ~3u));
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(hi) : "r"((a & ~3u) + 4u));
+#endif
         return __funnelshift_r(lo, hi, (a & 3u) * 8u);
     }
     __device__ __forceinline__ uint32_t ld1_far(int i) const { return ld1(i); }

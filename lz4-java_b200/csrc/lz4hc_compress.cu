@@ -91,7 +91,7 @@ lz4hc_compress_kernel(const uint8_t* __restrict__ src_base, const uint64_t* __re
                       uint8_t* __restrict__ dst_base, const uint64_t* __restrict__ dst_off,
                       const int32_t* __restrict__ dst_cap, int32_t* __restrict__ result, uint32_t nblocks, int level)
 {
-    extern __shared__ __align__(16) uint8_t smem_raw[];
+    B200_DYN_SMEM(smem_raw, 16);
     HcTable t;
     t.ring = reinterpret_cast<uint16_t*>(smem_raw);
     t.head = reinterpret_cast<uint32_t*>(smem_raw + (size_t(2) << BL) * WAYS);
@@ -179,6 +179,7 @@ lz4hc_compress_kernel(const uint8_t* __restrict__ src_base, const uint64_t* __re
     }
 }
 
+#ifndef B200_HOST_SIM          // knobs and launchers: CUDA only
 extern "C" {
 int b200lz4_hc_bucket_log = 11;   // 11 = 2048 buckets, 10 = 1024 buckets
 int b200lz4_hc_ways = 32;         // 32 = one position per warp (128 KiB table at 2048 buckets, 1 CTA/SM, best ratio);
@@ -204,5 +205,7 @@ cudaError_t launch_compress_hc(const BatchArgs& a, int level, cudaStream_t st)
     if (b200lz4_hc_ways == 16) return b200lz4_hc_bucket_log == 10 ? launch_hc<10, 16>(a, level, st) : launch_hc<11, 16>(a, level, st);
     return b200lz4_hc_bucket_log == 10 ? launch_hc<10, 32>(a, level, st) : launch_hc<11, 32>(a, level, st);
 }
+
+#endif
 
 } // namespace b200

@@ -53,6 +53,7 @@ __device__ __forceinline__ uint64_t finish64(uint64_t h, const uint8_t* p, uint3
     return h;
 }
 
+#ifndef B200_HOST_SIM          // PTX: not part of the emulated build (tests/simt)
 // ---- mbarrier / TMA bulk-copy primitives (PTX; SASS: SYNCS.*, UBLKCP)
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
@@ -72,6 +73,8 @@ __device__ __forceinline__ void tma_bulk_g2s(uint32_t dst_smem, const void* src_
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  :: "r"(dst_smem), "l"(src_gmem), "r"(bytes), "r"(bar) : "memory");
 }
+
+#endif
 
 template <int BITS> struct XxhTraits;
 template <> struct XxhTraits<32> { using word = uint32_t; static constexpr int STRIPE = 16; };
@@ -105,6 +108,7 @@ template <> struct Acc<64> {
     }
 };
 
+#ifndef B200_HOST_SIM          // TMA-staged batch kernel and its launchers: CUDA only
 static constexpr int XXH_WARPS = 4;
 static constexpr int XXH_CHUNK = 256;                    // bytes per lane per stage
 static constexpr int XXH_SLOT  = XXH_CHUNK + 16;         // slot stride: 16-byte LDS conflict-free
@@ -208,6 +212,8 @@ cudaError_t launch_xxh64(const uint8_t* base, const uint64_t* off, const int32_t
     return cudaGetLastError();
 }
 
+#endif
+
 // ------------------------------------------------------------------ one long XXH32 stream per warp
 // A single XXH32 stream is four serial accumulator chains (xxhash.c:269-275: acc = rotl(acc + w*P2, 13) * P1,
 // ~10 cycles per 16-byte stripe), so one stream cannot go faster than ~3 GB/s on this clock whatever feeds it.
@@ -294,6 +300,7 @@ xxh32_long_kernel(const uint8_t* __restrict__ base, const uint64_t* __restrict__
     if (lane == 0) out[i] = finish32(h + L, p + 16 * stripes, L & 15u);
 }
 
+#ifndef B200_HOST_SIM
 cudaError_t launch_xxh32_long(const uint8_t* base, const uint64_t* off, const int32_t* len, uint32_t seed,
                               uint32_t* out, size_t n, cudaStream_t st)
 {
@@ -301,6 +308,7 @@ cudaError_t launch_xxh32_long(const uint8_t* base, const uint64_t* off, const in
     xxh32_long_kernel<<<(unsigned)n, 32, 0, st>>>(base, off, len, seed, out, (uint32_t)n);
     return cudaGetLastError();
 }
+#endif
 
 // ---- the same for XXH64: stripes of 32 bytes, rows of 256 bytes (one 64-bit word per lane), chain = lane & 3.
 __device__ __forceinline__ uint64_t xxh64_chain_init(uint64_t seed, int lane)
@@ -386,6 +394,7 @@ xxh64_long_kernel(const uint8_t* __restrict__ base, const uint64_t* __restrict__
     if (lane == 0) out[i] = finish64(h + uint64_t(L), p + 32 * stripes, L & 31u);
 }
 
+#ifndef B200_HOST_SIM
 cudaError_t launch_xxh64_long(const uint8_t* base, const uint64_t* off, const int32_t* len, uint64_t seed,
                               uint64_t* out, size_t n, cudaStream_t st)
 {
@@ -393,6 +402,7 @@ cudaError_t launch_xxh64_long(const uint8_t* base, const uint64_t* off, const in
     xxh64_long_kernel<<<(unsigned)n, 32, 0, st>>>(base, off, len, seed, out, (uint32_t)n);
     return cudaGetLastError();
 }
+#endif
 
 // ------------------------------------------------------------------ streaming state (device-resident)
 // One lane walks the XXH32_update / XXH64_update state machine (xxhash.c:515-546, 971-1002); the
@@ -493,6 +503,7 @@ __global__ void xxh64_stream_kernel(Xxh64State* s, int op, uint64_t seed, const 
     }
 }
 
+#ifndef B200_HOST_SIM
 cudaError_t launch_xxh32_stream(Xxh32State* st, int op, uint32_t seed, const uint8_t* data, size_t len, cudaStream_t s)
 {
     xxh32_stream_kernel<<<1, 32, 0, s>>>(st, op, seed, data, len);
@@ -503,5 +514,6 @@ cudaError_t launch_xxh64_stream(Xxh64State* st, int op, uint64_t seed, const uin
     xxh64_stream_kernel<<<1, 32, 0, s>>>(st, op, seed, data, len);
     return cudaGetLastError();
 }
+#endif
 
 } // namespace b200

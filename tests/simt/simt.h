@@ -61,8 +61,13 @@ static inline unsigned long max(unsigned long a, unsigned long b) { return a > b
 static inline int __ffs(int x) { return x ? __builtin_ctz((unsigned)x) + 1 : 0; }
 static inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
+static inline int __ffsll(long long x) { return x ? __builtin_ctzll((unsigned long long)x) + 1 : 0; }
+static inline int __clzll(long long x) { return x ? __builtin_clzll((unsigned long long)x) : 64; }
+static inline int __popcll(unsigned long long x) { return __builtin_popcountll(x); }
 static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t s) { return (uint32_t)((((uint64_t)hi << 32) | lo) >> (s & 31)); }
 static inline uint32_t __funnelshift_l(uint32_t lo, uint32_t hi, uint32_t s) { return (uint32_t)(((((uint64_t)hi << 32) | lo) << (s & 31)) >> 32); }
+static inline size_t __cvta_generic_to_shared(const void* p) { return (size_t)p; }
+static inline size_t __cvta_generic_to_global(const void* p) { return (size_t)p; }
 static inline void __threadfence_block() {}
 static inline void __threadfence() {}
 static inline unsigned atomicAdd(unsigned* p, unsigned v) { unsigned o = *p; *p = o + v; return o; }
@@ -93,6 +98,7 @@ struct Cta {
 };
 
 inline Cta*& cta() { static Cta* c = nullptr; return c; }
+inline uint8_t* dyn_smem() { alignas(128) static uint8_t mem[232448]; return mem; }     // the CTA's dynamic shared memory
 inline Lane*& cur() { static Lane* l = nullptr; return l; }
 inline ucontext_t& sched_ctx() { static ucontext_t c; return c; }
 
@@ -209,14 +215,25 @@ inline void launch(unsigned grid, int nthreads, std::function<void()> body)
     for (unsigned b = 0; b < grid; b++) run_cta(nthreads, Idx{b, 0, 0}, Idx{grid, 1, 1}, body);
 }
 
-template <class T> inline uint32_t bits(T v) { static_assert(sizeof(T) <= 4, "32-bit shuffles only"); uint32_t u = 0; std::memcpy(&u, &v, sizeof(T)); return u; }
+template <class T> inline uint32_t bits(T v) { static_assert(sizeof(T) <= 4, "32-bit payload"); uint32_t u = 0; std::memcpy(&u, &v, sizeof(T)); return u; }
 template <class T> inline T unbits(uint32_t u) { T v; std::memcpy(&v, &u, sizeof(T)); return v; }
 inline int lane_of() { return cur()->tid & 31; }
 
-template <class T> inline T shfl(int line, unsigned, T v, int src) { return unbits<T>(warp_op(OP_SHFL, line, bits(v), src & 31)); }
-template <class T> inline T shfl_xor(int line, unsigned, T v, int m) { return unbits<T>(warp_op(OP_SHFL, line, bits(v), lane_of() ^ m)); }
-template <class T> inline T shfl_up(int line, unsigned, T v, int d) { const int s = lane_of() - d; return unbits<T>(warp_op(OP_SHFL, line, bits(v), s < 0 ? lane_of() : s)); }
-template <class T> inline T shfl_down(int line, unsigned, T v, int d) { const int s = lane_of() + d; return unbits<T>(warp_op(OP_SHFL, line, bits(v), s > 31 ? lane_of() : s)); }
+// 32-bit payloads directly, 64-bit ones (CUDA allows long long / double) as two shuffles
+template <class T> inline T shfl_src(int line, T v, int src)
+{
+    if constexpr (sizeof(T) <= 4) return unbits<T>(warp_op(OP_SHFL, line, bits(v), src));
+    else {
+        static_assert(sizeof(T) == 8, "shuffle payload");
+        uint64_t u; std::memcpy(&u, &v, 8);
+        const uint64_t lo = warp_op(OP_SHFL, line, (uint32_t)u, src), hi = warp_op(OP_SHFL, line, (uint32_t)(u >> 32), src);
+        u = lo | (hi << 32); T r; std::memcpy(&r, &u, 8); return r;
+    }
+}
+template <class T> inline T shfl(int line, unsigned, T v, int src) { return shfl_src(line, v, src & 31); }
+template <class T> inline T shfl_xor(int line, unsigned, T v, int m) { return shfl_src(line, v, lane_of() ^ m); }
+template <class T> inline T shfl_up(int line, unsigned, T v, int d) { const int s = lane_of() - d; return shfl_src(line, v, s < 0 ? lane_of() : s); }
+template <class T> inline T shfl_down(int line, unsigned, T v, int d) { const int s = lane_of() + d; return shfl_src(line, v, s > 31 ? lane_of() : s); }
 
 } // namespace simt
 

@@ -1,10 +1,11 @@
-"""The CUDA decoder kernels' own source, run on the CPU by a SIMT emulator (tests/simt/simt.h), against the oracle.
+"""The CUDA kernels' own source, run on the CPU by a SIMT emulator (tests/simt/simt.h), against the oracle.
 
-No GPU is involved and nothing here is a product path: lz4-java_b200/csrc/lz4_decompress.cu is compiled as host C++
-with -DB200_HOST_SIM (every CUDA thread of a CTA becomes a coroutine; warp collectives and barriers are emulated),
-and the four kernels — safe/fast x batched/sequential — are fuzzed on inputs the GPU tests also use.  This checks the
-kernels' logic (token walk, margins, dependency rounds, the reference's accept/reject rules and return codes), not
-timing or the GPU memory model.  It exists because the build box has no GPU: a logic bug in the batched decoder
+No GPU is involved and nothing here is a product path: the .cu files of lz4-java_b200/csrc are compiled as host C++
+with -DB200_HOST_SIM (every CUDA thread of a CTA becomes a coroutine; warp collectives, __syncthreads and the named
+barriers of the two-warp compressor are emulated; a deadlock or a divergent full-mask collective aborts).  The four
+decoder kernels — safe/fast x batched/sequential — and the fast-compress kernels (algos 1-3, all table variants) are
+fuzzed on inputs the GPU tests also use.  This checks the kernels' logic (token walk, margins, dependency rounds,
+the reference's accept/reject rules and return codes, the parser/lookup hand-off), not timing or the GPU memory model.  It exists because the build box has no GPU: a logic bug in the batched decoder
 (a long sequence early in a batch pushing later ones past the output margin) was found late in round 1 by a GPU
 sweep; on the pre-fix source this file's test_walk_stops_at_the_stream_end fails on the same six blocks a CPU model
 predicted, on the fixed source it passes."""
@@ -23,19 +24,45 @@ ROOT = os.path.dirname(HERE)
 PAD = 4096
 
 
-@pytest.fixture(scope="module")
-def sim():
+def _build(harness, so_name):
     out = os.path.join(HERE, "simt", "_build")
     os.makedirs(out, exist_ok=True)
-    so = os.path.join(out, "libdecsim.so")
+    so = os.path.join(out, so_name)
     cmd = ["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-Wno-unknown-pragmas", "-Wno-attributes", "-DB200_HOST_SIM",
            "-I" + os.path.join(HERE, "simt"), "-I" + os.path.join(ROOT, "lz4-java_b200", "csrc"),
-           os.path.join(HERE, "simt", "dec_harness.cpp"), "-o", so]
+           os.path.join(HERE, "simt", harness), "-o", so]
     subprocess.run(cmd, check=True, capture_output=True)
-    lib = ctypes.CDLL(so)
+    return ctypes.CDLL(so)
+
+
+@pytest.fixture(scope="module")
+def sim():
+    lib = _build("dec_harness.cpp", "libdecsim.so")
     for f in (lib.sim_decompress_safe, lib.sim_decompress_fast):
         f.restype = ctypes.c_int
         f.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+    return lib
+
+
+@pytest.fixture(scope="module")
+def msim():
+    lib = _build("misc_harness.cpp", "libmiscsim.so")
+    lib.sim_compress_hc.restype = ctypes.c_int
+    lib.sim_compress_hc.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    lib.sim_xxh32_long.restype = ctypes.c_uint32; lib.sim_xxh32_long.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32]
+    lib.sim_xxh64_long.restype = ctypes.c_uint64; lib.sim_xxh64_long.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64]
+    lib.sim_xxh32_stream.restype = ctypes.c_uint32
+    lib.sim_xxh32_stream.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_int]
+    lib.sim_xxh64_stream.restype = ctypes.c_uint64
+    lib.sim_xxh64_stream.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_int]
+    return lib
+
+
+@pytest.fixture(scope="module")
+def csim():
+    lib = _build("comp_harness.cpp", "libcompsim.so")
+    lib.sim_compress_fast.restype = ctypes.c_int
+    lib.sim_compress_fast.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int] + [ctypes.c_int] * 5
     return lib
 
 
@@ -186,3 +213,88 @@ def test_dependency_patterns_and_extremes(sim, port, batched):
         assert r == len(d) and o == d, (k, r)
         r, o = run_fast(sim, c, len(d), batched, readable=c + bytes(3000))
         assert r == len(c) and o == d, (k, r)
+
+
+# ---------------------------------------------------------------------------------------------- fast compress
+COMPRESS_VARIANTS = {            # name: (algo, hash_log, u16 table, sparse, staged input)
+    "v3_hl13": (3, 13, 1, 0, 0), "v3_hl12": (3, 12, 1, 0, 0), "v3_hl13_sparse": (3, 13, 1, 1, 0), "v3_hl12_sparse": (3, 12, 1, 1, 0),
+    "v2_u16": (2, 13, 1, 0, 0), "v2_u16_hl12": (2, 12, 1, 0, 0), "v2_u32": (2, 12, 0, 0, 0),
+    "v1_u16": (1, 13, 1, 0, 0), "v1_staged": (1, 13, 1, 0, 1), "v1_u32": (1, 12, 0, 0, 0),
+}
+
+
+def run_compress(csim, d, cap, variant):
+    algo, hl, u16, sparse, stage = COMPRESS_VARIANTS[variant]
+    s = _src(d); o = np.full(max(cap, 0) + 2 * PAD, 0x55, dtype=np.uint8)
+    r = csim.sim_compress_fast(s.ctypes.data + PAD, len(d), o.ctypes.data + PAD, cap, algo, hl, u16, sparse, stage)
+    assert (o[:PAD] == 0x55).all() and (o[PAD + max(cap, 0):] == 0x55).all(), "wrote outside [dst, dst+cap)"
+    return r, o[PAD:PAD + max(r, 0)].tobytes()
+
+
+@pytest.mark.parametrize("variant", list(COMPRESS_VARIANTS))
+def test_compress_kernels_emit_valid_blocks(csim, port, variant):
+    u16 = COMPRESS_VARIANTS[variant][2]
+    tot = ctot = 0
+    for name, d in corpus.blocks(port):
+        if len(d) > 70000 or (u16 and len(d) >= 65536 + 11):
+            continue
+        r, c = run_compress(csim, d, port.compress_bound(len(d)), variant)
+        assert r > 0, (variant, name)
+        rr, o = port.decompress_safe(c, len(d))
+        assert rr == len(d) and o == d, (variant, name, len(d), rr)
+        tot += len(d); ctot += r
+    assert tot / ctot > 1.9                      # the corpus compresses about 2.0-2.35x with every variant
+
+
+@pytest.mark.parametrize("variant", ["v3_hl13", "v2_u16", "v1_u16"])
+def test_compress_limited_output_never_overruns(csim, port, variant):
+    """maxDestLen below the bound (lz4.c:1085-1088, 1158, 1269-1279): either a valid block that fits, or 0"""
+    rng = random.Random(5)
+    picks = [d for _, d in corpus.blocks(port, big=False)][::5]
+    for d in picks:
+        full, _ = run_compress(csim, d, port.compress_bound(len(d)), variant)
+        for cap in sorted({0, 1, full - 1, full, full + 1, max(0, full // 2), max(0, full - 17), rng.randrange(0, full + 20)}):
+            r, c = run_compress(csim, d, cap, variant)
+            assert 0 <= r <= cap
+            if r > 0:
+                rr, o = port.decompress_safe(c, len(d))
+                assert rr == len(d) and o == d
+            elif cap >= full:
+                raise AssertionError(("fits but was refused", len(d), cap, full))
+
+
+# ---------------------------------------------------------------------------------------------- HC, long-stream / streaming XXH
+def test_long_stream_and_streaming_xxh_kernels(msim, port):
+    """xxh32_long_kernel / xxh64_long_kernel (one warp per stream) and the warp-cooperative streaming updates:
+    every alignment phase, lengths around the stripe / row / group boundaries, random chunkings, digest mid-stream"""
+    rng = random.Random(3)
+    sizes = [0, 1, 3, 4, 15, 16, 17, 31, 32, 33, 63, 64, 127, 128, 129, 255, 256, 257, 1023, 1024, 1025, 4096, 5000, 8191, 8192, 8193, 40000, 70001]
+    for trial, n0 in enumerate(sizes * 2):
+        n = n0 + (rng.randrange(0, 40) if trial >= len(sizes) else 0)
+        ph = trial % 8
+        d = rng.randbytes(n)
+        a = np.zeros(n + 2 * PAD, dtype=np.uint8); a[PAD + ph:PAD + ph + n] = np.frombuffer(d, dtype=np.uint8)
+        ptr = a.ctypes.data + PAD + ph
+        for seed in (0, 0x9747B28C):
+            assert msim.sim_xxh32_long(ptr, n, seed) == port.xxh32(d, seed), (n, ph, seed)
+            assert msim.sim_xxh64_long(ptr, n, seed) == port.xxh64(d, seed), (n, ph, seed)
+        cuts = sorted(rng.randrange(0, n + 1) for _ in range(rng.randrange(0, 6)))
+        ca = (ctypes.c_int * max(1, len(cuts)))(*cuts)
+        assert msim.sim_xxh32_stream(ptr, n, 7, ca, len(cuts)) == port.xxh32(d, 7), (n, cuts)
+        assert msim.sim_xxh64_stream(ptr, n, 7, ca, len(cuts)) == port.xxh64(d, 7), (n, cuts)
+
+
+@pytest.mark.parametrize("table", [(11, 32), (10, 16)], ids=["2048x32", "1024x16"])
+def test_hc_kernel_emits_valid_blocks(msim, port, table):
+    bl, ways = table
+    picks = [(n, d) for n, d in corpus.blocks(port, big=False) if len(d) <= 8192][::2]
+    assert len(picks) > 15
+    for name, d in picks:
+        bound = port.compress_bound(len(d))
+        s = _src(d); o = np.full(bound + 2 * PAD, 0x55, dtype=np.uint8)
+        r = msim.sim_compress_hc(s.ctypes.data + PAD, len(d), o.ctypes.data + PAD, bound, 9, bl, ways)
+        assert r > 0 and (o[:PAD] == 0x55).all() and (o[PAD + bound:] == 0x55).all(), (name, r)
+        rr, oo = port.decompress_safe(o[PAD:PAD + r].tobytes(), len(d))
+        assert rr == len(d) and oo == d, (name, bl, ways)
+        if len(d) >= 2048 and name.startswith(("rdg", "text", "rand3")):
+            assert r <= len(port.compress(d)) * 1.02, (name, r)          # never meaningfully worse than the fast parse
