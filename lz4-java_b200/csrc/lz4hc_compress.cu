@@ -182,6 +182,7 @@ lz4hc_compress_kernel(const uint8_t* __restrict__ src_base, const uint64_t* __re
 #ifndef B200_HOST_SIM          // knobs and launchers: CUDA only
 extern "C" {
 int b200lz4_hc_bucket_log = 11;   // 11 = 2048 buckets, 10 = 1024 buckets
+int b200lz4_hc_algo = 1;          // 1 = this file (default); 2 = lz4hc2_compress.cu (experimental: search everything, DP parse)
 int b200lz4_hc_ways = 32;         // 32 = one position per warp (128 KiB table at 2048 buckets, 1 CTA/SM, best ratio);
                                   // 16 = one position per half-warp, 8 positions per round (64 KiB, 3 CTAs/SM)
 }
@@ -202,6 +203,7 @@ cudaError_t launch_compress_hc(const BatchArgs& a, int level, cudaStream_t st)
 {
     if (a.n == 0) return cudaSuccess;
     if (level < 1) level = 9;                                                 // LZ4HC_CLEVEL_DEFAULT, lz4hc.c:840
+    if (b200lz4_hc_algo == 2) return launch_compress_hc2(a, st);
     if (b200lz4_hc_ways == 16) return b200lz4_hc_bucket_log == 10 ? launch_hc<10, 16>(a, level, st) : launch_hc<11, 16>(a, level, st);
     return b200lz4_hc_bucket_log == 10 ? launch_hc<10, 32>(a, level, st) : launch_hc<11, 32>(a, level, st);
 }

@@ -480,6 +480,32 @@ def test_hc_compress_roundtrip_and_ratio(b200, checker):
         assert checker.decompress_safe(c, len(d))[1] == d
 
 
+@pytest.mark.skipif(not __import__("os").environ.get("B200_EXPERIMENTAL"),
+                    reason="lz4hc2_compress.cu has only run on the CPU emulator so far (tests/test_kernel_logic_cpu.py); "
+                           "set B200_EXPERIMENTAL=1 to run it on the GPU")
+def test_hc_second_design_on_gpu(b200, checker):
+    """b200lz4_hc_algo = 2 (search every position, DP parse): same contract as the default HC kernel, and a ratio at least
+    as good on the same inputs"""
+    items = [(nm, d) for nm, d in corpus.blocks(checker) if len(d) in (0, 1, 12, 13, 64, 1000, 4096, 65536) or nm.startswith("period")]
+    items += [(f"rdg256k_{mp}", checker.datagen(262144, mp, 0.0, 4).tobytes()) for mp in (0.2, 0.5, 0.8)]
+    items += corpus.calgary_blocks(2)
+    src, soff, slen = corpus.pack([d for _, d in items])
+    bounds = [b200.max_compressed_length(len(d)) for _, d in items]
+    doff, dcap, total = _slots(bounds)
+    first = b200.batch.compress_hc_batch_host(src, soff, slen, np.zeros(total, dtype=np.uint8), doff, dcap, level=9)
+    _knob(b200, "b200lz4_hc_algo", 2)
+    try:
+        dst = np.zeros(total, dtype=np.uint8)
+        res = b200.batch.compress_hc_batch_host(src, soff, slen, dst, doff, dcap, level=9)
+    finally:
+        _knob(b200, "b200lz4_hc_algo", 1)
+    for k, (name, d) in enumerate(items):
+        assert 0 < res[k] <= bounds[k], (name, int(res[k]))
+        r, out = checker.decompress_safe(dst[int(doff[k]):int(doff[k]) + int(res[k])].tobytes(), len(d))
+        assert r == len(d) and out == d, name
+    assert int(res.sum()) <= int(first.sum()) * 1.005, (int(res.sum()), int(first.sum()))
+
+
 def test_frame_batch_decoder(b200, port):
     """LZ4 Frame container (config 3's driver): frames written by the oracle (and by the reference's
     LZ4F_compressFrame when available) decode bit-exactly; every checksum / truncation error of

@@ -49,6 +49,8 @@ def msim():
     lib = _build("misc_harness.cpp", "libmiscsim.so")
     lib.sim_compress_hc.restype = ctypes.c_int
     lib.sim_compress_hc.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    lib.sim_compress_hc2.restype = ctypes.c_int
+    lib.sim_compress_hc2.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
     lib.sim_xxh32_long.restype = ctypes.c_uint32; lib.sim_xxh32_long.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32]
     lib.sim_xxh64_long.restype = ctypes.c_uint64; lib.sim_xxh64_long.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint64]
     lib.sim_xxh32_stream.restype = ctypes.c_uint32
@@ -298,3 +300,46 @@ def test_hc_kernel_emits_valid_blocks(msim, port, table):
         assert rr == len(d) and oo == d, (name, bl, ways)
         if len(d) >= 2048 and name.startswith(("rdg", "text", "rand3")):
             assert r <= len(port.compress(d)) * 1.02, (name, r)          # never meaningfully worse than the fast parse
+
+
+def _hc2(msim, d, cap, max_block=262144):
+    s = _src(d); o = np.full(max(cap, 0) + 2 * PAD, 0x55, dtype=np.uint8)
+    r = msim.sim_compress_hc2(s.ctypes.data + PAD, len(d), o.ctypes.data + PAD, cap, max_block)
+    assert (o[:PAD] == 0x55).all() and (o[PAD + max(cap, 0):] == 0x55).all(), "wrote outside [dst, dst+cap)"
+    return r, o[PAD:PAD + max(r, 0)].tobytes()
+
+
+def test_hc_second_design_search_parse_layout(msim, port, checker):
+    """lz4hc2_compress.cu (experimental, b200lz4_hc_algo = 2): K1 search of every position, K2 DP parse, K3 layout.
+    Valid blocks on the corpus, capacity handling, refusal above the arena's block limit, and the ratio the design
+    model promises: not below the first design's lazy parse, within 2 % of LZ4_compress_HC(9) on one 32 KiB generator block."""
+    for name, d in corpus.blocks(port, big=False)[::4]:
+        if len(d) > 8192:
+            continue
+        bound = port.compress_bound(len(d))
+        r, c = _hc2(msim, d, bound)
+        assert r > 0, (name, r)
+        rr, o = port.decompress_safe(c, len(d))
+        assert rr == len(d) and o == d, (name, len(d), rr)
+        if len(d) > 64:
+            r2, c2 = _hc2(msim, d, r - 1)                       # one byte too small: refused, nothing written past cap
+            assert r2 == 0, (name, r, r2)
+            r3, c3 = _hc2(msim, d, r)                           # exactly enough
+            assert r3 == r and c3 == c, name
+    d = bytes(range(256)) * 40
+    assert _hc2(msim, d, port.compress_bound(len(d)), max_block=4096)[0] == 0          # longer than the arena allows: refused
+    d = port.datagen(32768, 0.5, 0.0, 4).tobytes()
+    r, c = _hc2(msim, d, port.compress_bound(len(d)))
+    rr, o = port.decompress_safe(c, len(d))
+    assert rr == len(d) and o == d
+    assert r < len(port.compress(d)) * 0.95                     # clearly denser than the fast parse
+    if hasattr(checker, "compress_hc"):                         # the reference build is present
+        ref = len(checker.compress_hc(d, 9))
+        assert r <= ref * 1.02, (r, ref)
+    # a block that starts with a run: the ring of the run's bucket holds only future positions of the first
+    # super-chunk — the neighbour candidates (nearest same-hash lane, p - 1) must find it
+    d = bytes([65]) * 700 + port.datagen(8000, 0.5, 0.0, 9).tobytes()
+    r, c = _hc2(msim, d, port.compress_bound(len(d)))
+    rr, o = port.decompress_safe(c, len(d))
+    assert rr == len(d) and o == d
+    assert c[0] >> 4 == 1 and (c[0] & 15) == 15 and c[2:4] == b"\x01\x00"        # 1 literal, then a long match at distance 1

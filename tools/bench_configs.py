@@ -127,6 +127,18 @@ def config4(chk, out):
         res[f"buckets_{1 << bl}_ways_{ways}"] = {"GiBps": nblk * bs / t / GIB, "ratio": nblk * bs / csum}
     C.c_int.in_dll(L._native.lib(), "b200lz4_hc_bucket_log").value = 11
     C.c_int.in_dll(L._native.lib(), "b200lz4_hc_ways").value = 32
+    if os.environ.get("B200_EXPERIMENTAL"):            # second design (lz4hc2_compress.cu): not yet run on a GPU in round 1
+        C.c_int.in_dll(L._native.lib(), "b200lz4_hc_algo").value = 2
+        try:
+            t = timeit(lambda: L.batch.compress_hc_batch_dev(src, soff, slen, comp, coff, ccap, clen, 9), iters=2, warm=1)
+            csum = int(clen.sum().item())
+            out_ = torch.zeros(nblk * bs, device=dev, dtype=torch.uint8); r_ = torch.zeros(nblk, device=dev, dtype=torch.int32)
+            L.batch.decompress_safe_batch_dev(comp, coff, clen, out_, soff, slen, r_)
+            ok = bool((r_ == bs).all().item()) and bool(torch.equal(out_, src))
+            del out_
+            res["second_design_search_all_dp_parse"] = {"GiBps": nblk * bs / t / GIB, "ratio": nblk * bs / csum, "roundtrip": ok}
+        finally:
+            C.c_int.in_dll(L._native.lib(), "b200lz4_hc_algo").value = 1
     ref_c = sum(len(chk.compress_hc(host[i * bs:(i + 1) * bs], 9)) for i in range(8)) if hasattr(chk, "compress_hc") else None
     t0 = time.perf_counter()
     if hasattr(chk, "compress_hc"):
