@@ -48,6 +48,7 @@ compact_gather_kernel(const uint8_t* __restrict__ slots, const uint64_t* __restr
     if (len > 0) warp_copy(out + out_off[b], slots + slot_off[b], len, lane_id());
 }
 
+#ifndef B200_HOST_SIM          // launchers: CUDA only
 cudaError_t launch_compact(const uint8_t* slots, const uint64_t* slot_off, const int32_t* lens,
                            uint8_t* out, uint64_t* out_off, uint64_t* total, size_t n, cudaStream_t st)
 {
@@ -65,5 +66,7 @@ cudaError_t launch_gather(const uint8_t* src, const uint64_t* src_off, const int
     compact_gather_kernel<<<(unsigned)((n + 3) / 4), 128, 0, st>>>(src, src_off, lens, dst, dst_off, (uint32_t)n);
     return cudaGetLastError();
 }
+
+#endif
 
 } // namespace b200

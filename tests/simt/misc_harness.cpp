@@ -69,3 +69,12 @@ extern "C" int sim_compress_hc2(const uint8_t* src, int n, uint8_t* dst, int cap
     simt::launch(1, 128, [&] { lz4hc2_layout_kernel(src, &zero, &sl, dst, &zero, &dc, &res, 0u, 1u, rec.data(), rec_stride, &cnt); });
     return res;
 }
+
+// ---- compaction (scan + gather)
+#include "../../lz4-java_b200/csrc/compact.cu"
+
+extern "C" void sim_compact(const uint8_t* slots, const uint64_t* slot_off, const int32_t* lens, uint8_t* out, uint64_t* out_off, uint64_t* total, uint32_t n)
+{
+    simt::launch(1, 1024, [&] { compact_scan_kernel(lens, out_off, total, n); });
+    simt::launch((n + 3) / 4, 128, [&] { compact_gather_kernel(slots, slot_off, lens, out, out_off, n); });
+}

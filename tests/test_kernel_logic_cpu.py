@@ -49,6 +49,8 @@ def msim():
     lib = _build("misc_harness.cpp", "libmiscsim.so")
     lib.sim_compress_hc.restype = ctypes.c_int
     lib.sim_compress_hc.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    lib.sim_compact.restype = None
+    lib.sim_compact.argtypes = [ctypes.c_void_p] * 6 + [ctypes.c_uint32]
     lib.sim_compress_hc2.restype = ctypes.c_int
     lib.sim_compress_hc2.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
     lib.sim_xxh32_long.restype = ctypes.c_uint32; lib.sim_xxh32_long.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_uint32]
@@ -343,3 +345,20 @@ def test_hc_second_design_search_parse_layout(msim, port, checker):
     rr, o = port.decompress_safe(c, len(d))
     assert rr == len(d) and o == d
     assert c[0] >> 4 == 1 and (c[0] & 15) == 15 and c[2:4] == b"\x01\x00"        # 1 literal, then a long match at distance 1
+
+
+def test_compaction_scan_and_gather(msim):
+    """compact.cu: exclusive scan of the lengths by one 1024-thread CTA (crossing its 1024-entry rounds), then the gather"""
+    rng = random.Random(12)
+    for n in (1, 2, 31, 32, 33, 1023, 1024, 1025, 2500):
+        lens = np.array([rng.choice([0, -3, 1, 5, 17, 40, 100, 333]) for _ in range(n)], dtype=np.int32)
+        stride = 352
+        slots = np.frombuffer(rng.randbytes(n * stride), dtype=np.uint8).copy()
+        slot_off = (np.arange(n, dtype=np.uint64) * stride)
+        out = np.full(int(np.maximum(lens, 0).sum()) + 64, 0x55, dtype=np.uint8)
+        out_off = np.zeros(n, dtype=np.uint64); total = np.zeros(1, dtype=np.uint64)
+        msim.sim_compact(slots.ctypes.data, slot_off.ctypes.data, lens.ctypes.data, out.ctypes.data, out_off.ctypes.data, total.ctypes.data, n)
+        want_off = np.concatenate([[0], np.cumsum(np.maximum(lens, 0))[:-1]]).astype(np.uint64)
+        assert (out_off == want_off).all() and int(total[0]) == int(np.maximum(lens, 0).sum()), n
+        packed = b"".join(slots[k * stride:k * stride + max(int(lens[k]), 0)].tobytes() for k in range(n))
+        assert out[:len(packed)].tobytes() == packed and (out[len(packed):] == 0x55).all(), n
