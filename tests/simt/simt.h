@@ -22,6 +22,7 @@
 #include <vector>
 #include <functional>
 #include <algorithm>
+#include <mutex>
 #include <ucontext.h>
 
 // ---- CUDA spellings
@@ -35,7 +36,38 @@
 #define __align__(n) __attribute__((aligned(n)))
 typedef int cudaError_t;
 typedef void* cudaStream_t;
-enum { cudaSuccess = 0 };
+typedef void* cudaEvent_t;
+enum { cudaSuccess = 0, cudaErrorNoDevice = 100, cudaErrorInsufficientDriver = 35, cudaErrorInitializationError = 3 };
+enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice, cudaMemcpyDefault };
+enum { cudaStreamNonBlocking = 1, cudaHostAllocDefault = 0, cudaEventDisableTiming = 2, cudaHostRegisterPortable = 1 };
+
+// ---- a stand-in for the slice of the CUDA runtime that the library's host layer (capi.cu, frame.cu) calls, so the whole
+// library can be built for the emulator (tests/simt/build_sim_library.sh).  Everything is synchronous; "device memory" is
+// host heap with 256-byte guard bands (the kernels read the aligned words around their buffers).
+namespace simt_rt {
+inline void* alloc(size_t n) { char* raw = (char*)std::calloc(n + 768, 1); if (!raw) return nullptr; char* p = raw + 256 + ((256 - ((uintptr_t)(raw + 256) & 255)) & 255); ((void**)p)[-1] = raw; return p; }
+inline void release(void* p) { if (p) std::free(((void**)p)[-1]); }
+}
+template <class T> static inline cudaError_t cudaMalloc(T** p, size_t n) { *p = (T*)simt_rt::alloc(n); return *p ? cudaSuccess : 2; }
+static inline cudaError_t cudaFree(void* p) { simt_rt::release(p); return cudaSuccess; }
+template <class T> static inline cudaError_t cudaHostAlloc(T** p, size_t n, unsigned) { *p = (T*)simt_rt::alloc(n); return *p ? cudaSuccess : 2; }
+static inline cudaError_t cudaFreeHost(void* p) { simt_rt::release(p); return cudaSuccess; }
+static inline cudaError_t cudaHostRegister(void*, size_t, unsigned) { return cudaSuccess; }
+static inline cudaError_t cudaHostUnregister(void*) { return cudaSuccess; }
+static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t = nullptr) { if (n) std::memmove(d, s, n); return cudaSuccess; }
+static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = nullptr) { std::memset(d, v, n); return cudaSuccess; }
+static inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
+static inline cudaError_t cudaSetDevice(int d) { return d == 0 ? cudaSuccess : 101; }
+static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
+static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = std::malloc(8); return cudaSuccess; }
+static inline cudaError_t cudaStreamDestroy(cudaStream_t s) { std::free(s); return cudaSuccess; }
+static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, unsigned) { *e = std::malloc(8); return cudaSuccess; }
+static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { std::free(e); return cudaSuccess; }
+static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t = nullptr) { return cudaSuccess; }
+static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+static inline const char* cudaGetErrorString(cudaError_t) { return "simt emulator"; }
 
 struct uint2 { uint32_t x, y; };
 struct uint4 { uint32_t x, y, z, w; };
@@ -209,9 +241,11 @@ inline void run_cta(int nthreads, Idx block, Idx grid, std::function<void()> bod
     cta() = nullptr; cur() = nullptr;
 }
 
-// grid of CTAs, one after the other
+// grid of CTAs, one after the other; launches from several host threads are serialised (the emulator's state is global)
+inline std::mutex& launch_mutex() { static std::mutex m; return m; }
 inline void launch(unsigned grid, int nthreads, std::function<void()> body)
 {
+    std::lock_guard<std::mutex> g(launch_mutex());
     for (unsigned b = 0; b < grid; b++) run_cta(nthreads, Idx{b, 0, 0}, Idx{grid, 1, 1}, body);
 }
 
