@@ -6,7 +6,9 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.environ.get("B200LZ4_SO") or os.path.join(_HERE, "libb200lz4.so")   # env override: sanitizer builds
+# B200LZ4_SO: a developer switch to load ANOTHER BUILD of the same library (sanitizer / variant builds, the emulator
+# build of tests/simt).  It is never set by the package and is not a fallback: without it only libb200lz4.so is tried.
+SO_PATH = os.environ.get("B200LZ4_SO") or os.path.join(_HERE, "libb200lz4.so")
 
 E_NODEVICE, E_CUDA, E_ARG = -1000001, -1000002, -1000003
 
