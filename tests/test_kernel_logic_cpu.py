@@ -362,3 +362,19 @@ def test_compaction_scan_and_gather(msim):
         assert (out_off == want_off).all() and int(total[0]) == int(np.maximum(lens, 0).sum()), n
         packed = b"".join(slots[k * stride:k * stride + max(int(lens[k]), 0)].tobytes() for k in range(n))
         assert out[:len(packed)].tobytes() == packed and (out[len(packed):] == 0x55).all(), n
+
+
+# ---------------------------------------------------------------------------------------------- the host layer too
+def test_host_layer_on_the_emulator_library():
+    """tests/simt/build_sim_library.sh builds the WHOLE library for the emulator (capi.cu / frame.cu / containers.cu
+    unchanged over a stand-in CUDA runtime); a few of the GPU parity tests then run against it in a subprocess (the
+    product loader of this process is left alone): the batch pipeline with bounce buffers and compaction, the
+    single-block factory API with its exception contract, streaming hashes.  The full file takes ~20 minutes this way
+    (see tests/simt/README.md); this is the one-minute slice."""
+    import sys
+    subprocess.run(["bash", os.path.join(HERE, "simt", "build_sim_library.sh")], check=True, capture_output=True)
+    env = dict(os.environ, B200LZ4_SO=os.path.join(HERE, "simt", "_build", "libb200lz4_sim.so"))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(HERE, "test_gpu_parity.py"), "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider",
+                        "-W", "ignore::DeprecationWarning", "-k", "factory_api or compact_host or xxhash_streaming or self_roundtrip"],
+                       env=env, cwd=ROOT, capture_output=True, text=True)
+    assert r.returncode == 0 and "4 passed" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
