@@ -6,9 +6,10 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-# B200LZ4_SO: a developer switch to load ANOTHER BUILD of the same library (sanitizer / variant builds, the emulator
-# build of tests/simt).  It is never set by the package and is not a fallback: without it only libb200lz4.so is tried.
-SO_PATH = os.environ.get("B200LZ4_SO") or os.path.join(_HERE, "libb200lz4.so")
+# The one library the package loads.  No environment switch here: tests/conftest.py and tools/_variant.py (development
+# infrastructure, outside the package) may point SO_PATH at another BUILD of the same library before first use — a
+# sanitizer / A-B variant build, or the emulator build of tests/simt — via B200LZ4_TEST_SO.
+SO_PATH = os.path.join(_HERE, "libb200lz4.so")
 
 E_NODEVICE, E_CUDA, E_ARG = -1000001, -1000002, -1000003
 

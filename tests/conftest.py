@@ -10,6 +10,12 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu under gpurun)")
+    # Development switch of the TEST harness (the package has none): run the suite against another build of the
+    # library — compute-sanitizer / variant builds, or tests/simt's emulator build on a box without a GPU.
+    alt = os.environ.get("B200LZ4_TEST_SO")
+    if alt:
+        import lz4java_b200._native as N
+        N.SO_PATH = os.path.abspath(alt)
 
 
 @pytest.fixture(scope="session")

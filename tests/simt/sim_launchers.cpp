@@ -4,7 +4,7 @@
 // sources; only the <<<...>>> launch sites are restated here, with the same dispatch rules as the real launchers.
 // TEST INFRASTRUCTURE ONLY: lets the host pipeline (chunking, bounce buffers, compaction, frame indexer, containers)
 // and most of tests/test_gpu_parity.py run on a box without a GPU:
-//     B200LZ4_SO=tests/simt/_build/libb200lz4_sim.so python -m pytest tests/test_gpu_parity.py -m gpu -k "not jni"
+//     B200LZ4_TEST_SO=tests/simt/_build/libb200lz4_sim.so python -m pytest tests/test_gpu_parity.py -m gpu -k "not jni"
 // The product never loads this library (it is not named libb200lz4.so and lives under tests/).
 #include "../../lz4-java_b200/csrc/lz4_decompress.cu"
 #include "../../lz4-java_b200/csrc/lz4_compress.cu"

@@ -69,3 +69,15 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".java")):
                 txt = open(os.path.join(dp, f), errors="ignore").read()
                 assert "oracle" not in txt.lower().replace("test oracle", ""), os.path.join(dp, f)
+
+
+def test_product_loader_has_no_library_switch(b200, monkeypatch):
+    """the package loads its own libb200lz4.so and nothing else: no environment variable can point it at another
+    library (the emulator build of tests/simt is reachable only through tests/conftest.py / tools/_variant.py)"""
+    pkg = os.path.join(ROOT, "lz4-java_b200")
+    for f in os.listdir(pkg):
+        if f.endswith(".py"):
+            txt = open(os.path.join(pkg, f)).read()
+            assert "os.environ" not in txt and "getenv" not in txt, f
+    if not os.environ.get("B200LZ4_TEST_SO"):
+        assert os.path.samefile(b200._native.SO_PATH, os.path.join(pkg, "libb200lz4.so"))

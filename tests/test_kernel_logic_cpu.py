@@ -373,7 +373,7 @@ def test_host_layer_on_the_emulator_library():
     (see tests/simt/README.md); this is the one-minute slice."""
     import sys
     subprocess.run(["bash", os.path.join(HERE, "simt", "build_sim_library.sh")], check=True, capture_output=True)
-    env = dict(os.environ, B200LZ4_SO=os.path.join(HERE, "simt", "_build", "libb200lz4_sim.so"))
+    env = dict(os.environ, B200LZ4_TEST_SO=os.path.join(HERE, "simt", "_build", "libb200lz4_sim.so"))
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(HERE, "test_gpu_parity.py"), "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider",
                         "-W", "ignore::DeprecationWarning", "-k", "factory_api or compact_host or xxhash_streaming or self_roundtrip"],
                        env=env, cwd=ROOT, capture_output=True, text=True)

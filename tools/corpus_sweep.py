@@ -6,6 +6,7 @@ import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
+import _variant  # noqa: F401  (B200LZ4_TEST_SO development switch)
 import lz4java_b200 as L
 from oracle import oracle as O
 

@@ -3,6 +3,7 @@ procedure, attribute every bad block to the compressor (CPU checker rejects the 
 import sys, os, ctypes, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
+import _variant  # noqa: F401  (B200LZ4_TEST_SO development switch)
 import lz4java_b200 as L
 from oracle import oracle as O
 BS = 65536

@@ -1,6 +1,7 @@
 import sys, os, time, threading
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
+import _variant  # noqa: F401  (B200LZ4_TEST_SO development switch)
 import lz4java_b200 as L
 from oracle import oracle as O
 B = L.batch; BLOCK = 65536
