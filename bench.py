@@ -116,6 +116,28 @@ def cpu_quota():
     return None
 
 
+def quota_cpus():
+    """CPUs the cgroup lets this container burn (cpu.max 'quota period'), or None when unlimited / unknown."""
+    q = cpu_quota()
+    try:
+        a, b = q.split()[:2]
+        return max(1, -(-int(a) // int(b)))
+    except Exception:
+        return None
+
+
+def thread_candidates():
+    """Thread counts tried for the CPU legs, so the reference gets its best operating point on this box: every
+    hardware thread, one per physical core, and — where a cgroup quota is far below the visible CPUs (oversubscribed
+    threads then lose time to CFS throttling) — the quota and twice the quota."""
+    n = cpu_threads()
+    c = {n, max(1, n // 2)}
+    q = quota_cpus()
+    if q and q < n:
+        c |= {min(n, q), min(n, 2 * q)}
+    return sorted(c, reverse=True)
+
+
 def cpu_roundtrip(chk, data, nblocks, threads, passes=3):
     """compress + fast-decompress `nblocks` blocks on `threads` host threads with the CPU library.
     Returns dict with GiB/s for each half, the round trip, and the ratio."""
@@ -148,7 +170,7 @@ def run_reference(args):
     nblocks = args.ref_blocks
     data = host_corpus(chk, nblocks)
     # pick the thread count that serves the reference best on this box (all SMT threads vs one per core)
-    cands = sorted({cpu_threads(), max(1, cpu_threads() // 2)}, reverse=True)
+    cands = thread_candidates()
     threads = max(cands, key=lambda t: cpu_roundtrip(chk, data, nblocks, t, passes=1)["roundtrip_gibs"])
     # W warm-up + K timed steps; each step = one bounded-sample round trip (best of 1 pass inside)
     for _ in range(args.warmup):
@@ -321,7 +343,7 @@ def run_b200(args):
             n_cpu = args.cpu_blocks
             cdata = host if base_blocks >= n_cpu else host_corpus(chk, n_cpu, seed=2)
             # all hardware threads, and one thread per physical core (SMT off-load): keep the better
-            cands = sorted({cpu_threads(), max(1, cpu_threads() // 2)}, reverse=True)
+            cands = thread_candidates()
             runs = [(cpu_roundtrip(chk, cdata, n_cpu, t, passes=3), t) for t in cands]
             r, threads = max(runs, key=lambda x: x[0]["roundtrip_gibs"])
             cpu = {"value": r["roundtrip_gibs"], "unit": UNIT, "cores": threads, "kind": chk.kind,
