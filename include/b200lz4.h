@@ -177,6 +177,11 @@ int     b200lz4_decompress_with_length(const char* src, int srcAvail, char* dst,
 uint64_t b200lz4_launch_count(void);
 void     b200lz4_launch_count_reset(void);
 
+/* pipeline contexts (3 streams + device staging each) created in this process so far.  A thread keeps one per device;
+ * contexts of threads that exited are reused by new threads, so with the reference's usage (any number of Java threads
+ * calling the singleton codecs, LZ4Compressor.java:25) this stays at the peak number of CONCURRENT callers. */
+int      b200lz4_context_count(void);
+
 #ifdef __cplusplus
 }
 #endif

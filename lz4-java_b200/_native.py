@@ -70,6 +70,7 @@ SYMBOLS = [
     ("b200lz4_decompress_with_length", _i, [_vp, _i, _vp, _i]),
     ("b200lz4_launch_count", _u64, []),
     ("b200lz4_launch_count_reset", None, []),
+    ("b200lz4_context_count", _i, []),
 ]
 
 _lib = None

@@ -36,7 +36,14 @@ static int ensure_device()
     cudaError_t e = cudaGetDeviceCount(&cnt);
     if (e != cudaSuccess) return fail_cuda(e, "cudaGetDeviceCount");
     if (cnt <= 0) { snprintf(tl_err, sizeof tl_err, "no CUDA device"); return B200LZ4_E_NODEVICE; }
-    if (tl_device < 0) tl_device = 0;
+    if (tl_device < 0) {
+        // no b200lz4_set_device() on this thread yet: adopt the thread's CURRENT device (0 on a fresh thread) instead of
+        // forcing device 0, so a caller that already selected a GPU (torch.cuda.set_device, cudaSetDevice) and hands
+        // us device pointers / its stream does not find its current device switched under it
+        int cur = 0;
+        if (cudaGetDevice(&cur) != cudaSuccess || cur < 0 || cur >= cnt) cur = 0;
+        tl_device = cur;
+    }
     CK(cudaSetDevice(tl_device));
     return 0;
 }
@@ -85,27 +92,84 @@ struct Ctx {
     uint8_t* h_bounce = nullptr; size_t bounce_cap = 0;    // pinned: [src | dst]
     ~Ctx() { /* process teardown frees device memory; explicit frees would race CUDA shutdown */ }
 };
-static thread_local Ctx* tl_ctx = nullptr;
+
+// Contexts (streams + staging) are owned by one thread at a time.  A thread keeps one per device it has used; when
+// the thread exits they go to a process-wide idle pool and the next new thread on that device picks them up, so a
+// server that churns threads (or a thread that alternates devices) does not grow device memory without bound.  No CUDA
+// call happens at thread exit (nothing here can race the runtime's own teardown); the pool itself is never destroyed.
+static std::atomic<int> g_contexts{0};
+struct CtxPool { std::mutex mu; std::vector<Ctx*> idle; };
+static CtxPool& ctx_pool() { static CtxPool* p = new CtxPool(); return *p; }
+struct ThreadCtxs {
+    std::vector<Ctx*> mine;
+    ~ThreadCtxs()
+    {
+        if (mine.empty()) return;
+        CtxPool& p = ctx_pool();
+        std::lock_guard<std::mutex> g(p.mu);
+        for (Ctx* c : mine) p.idle.push_back(c);
+    }
+};
+static thread_local ThreadCtxs tl_ctxs;
+static thread_local Ctx* tl_ctx = nullptr;          // the context of tl_device (cache of the lookup below)
 
 static int get_ctx(Ctx** out)
 {
     int rc = ensure_device();
     if (rc) return rc;
-    if (tl_ctx && tl_ctx->device != tl_device) { /* device switched: start a fresh context */ tl_ctx = nullptr; }
+    if (tl_ctx && tl_ctx->device != tl_device) tl_ctx = nullptr;        // device switched on this thread
+    if (!tl_ctx) {
+        for (Ctx* c : tl_ctxs.mine) if (c->device == tl_device) { tl_ctx = c; break; }
+    }
+    if (!tl_ctx) {
+        CtxPool& p = ctx_pool();
+        std::lock_guard<std::mutex> g(p.mu);
+        for (size_t k = 0; k < p.idle.size(); k++)
+            if (p.idle[k]->device == tl_device) { tl_ctx = p.idle[k]; p.idle.erase(p.idle.begin() + (long)k); break; }
+        if (tl_ctx) tl_ctxs.mine.push_back(tl_ctx);
+    }
     if (!tl_ctx) {
         Ctx* c = new (std::nothrow) Ctx();
         if (!c) return fail_arg("out of host memory");
         c->device = tl_device;
         for (int s = 0; s < NSLOTS; s++) {
-            CK(cudaStreamCreateWithFlags(&c->slot[s].st, cudaStreamNonBlocking));
-            CK(cudaEventCreateWithFlags(&c->slot[s].done, cudaEventDisableTiming));
-            CK(cudaEventCreateWithFlags(&c->slot[s].drained, cudaEventDisableTiming));
+            cudaError_t e = cudaStreamCreateWithFlags(&c->slot[s].st, cudaStreamNonBlocking);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->slot[s].done, cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->slot[s].drained, cudaEventDisableTiming);
+            if (e != cudaSuccess) {
+                for (int t = 0; t <= s; t++) {
+                    if (c->slot[t].st) cudaStreamDestroy(c->slot[t].st);
+                    if (c->slot[t].done) cudaEventDestroy(c->slot[t].done);
+                    if (c->slot[t].drained) cudaEventDestroy(c->slot[t].drained);
+                }
+                delete c;
+                return fail_cuda(e, "creating the pipeline streams");
+            }
         }
+        tl_ctxs.mine.push_back(c);
         tl_ctx = c;
+        g_contexts.fetch_add(1, std::memory_order_relaxed);
     }
     *out = tl_ctx;
     return 0;
 }
+
+// A pipeline call that fails half way (a CUDA error, or an argument error found at a later chunk) must not leave
+// chunks in flight: the next call on this thread would retire them into ITS result array with the old block indices.
+// The guard waits for whatever was queued and clears the slots' bookkeeping unless the call ran to completion.
+static void ctx_abandon(Ctx* c)
+{
+    for (int k = 0; k < NSLOTS; k++) {
+        Slot& s = c->slot[k];
+        if (s.busy || s.draining) cudaStreamSynchronize(s.st);       // result of the wait is irrelevant here
+        s.busy = false; s.draining = false; s.scatter = false;
+    }
+}
+struct PipelineGuard {
+    Ctx* c; bool completed = false;
+    explicit PipelineGuard(Ctx* c_) : c(c_) {}
+    ~PipelineGuard() { if (!completed) ctx_abandon(c); }
+};
 
 static int slot_reserve(Slot& s, size_t src_bytes, size_t dst_bytes, size_t nblocks, size_t aux_bytes = 0)
 {
@@ -180,6 +244,7 @@ static int host_batch(Op op, const uint8_t* src_base, const uint64_t* src_off, c
     if (n == 0) return 0;
     if (!src_base || !src_off || !src_len || !dst_base || !dst_off || !dst_cap || !result) return fail_arg("null pointer");
     Ctx* c; int rc = get_ctx(&c); if (rc) return rc;
+    PipelineGuard guard(c);
 
     size_t i0 = 0; int cur = 0;
     while (i0 < n) {
@@ -248,6 +313,7 @@ static int host_batch(Op op, const uint8_t* src_base, const uint64_t* src_off, c
         i0 = i1; cur = (cur + 1) % NSLOTS;
     }
     for (int k = 0; k < NSLOTS; k++) { rc = slot_retire(c->slot[(cur + k) % NSLOTS], result, dst_base, dst_off, dst_cap); if (rc) return rc; }
+    guard.completed = true;
     return 0;
 }
 
@@ -258,6 +324,7 @@ static int hash_host_batch(int bits, const uint8_t* base, const uint64_t* off, c
     if (n == 0) return 0;
     if (!base || !off || !len || !out) return fail_arg("null pointer");
     Ctx* c; int rc = get_ctx(&c); if (rc) return rc;
+    PipelineGuard guard(c);
     size_t i0 = 0; int cur = 0;
     while (i0 < n) {
         const uint64_t lo = off[i0]; uint64_t hi = lo; size_t i1 = i0;
@@ -298,6 +365,7 @@ static int hash_host_batch(int bits, const uint8_t* base, const uint64_t* off, c
             s.busy = false;
         }
     }
+    guard.completed = true;
     return 0;
 }
 
@@ -554,6 +622,7 @@ int b200lz4_compress_fast_compact_host(const uint8_t* src_base, const uint64_t* 
     if (n == 0) return 0;
     if (!src_base || !src_off || !src_len || !dst_base || !out_off || !result) return fail_arg("null pointer");
     Ctx* c; int rc = get_ctx(&c); if (rc) return rc;
+    PipelineGuard guard(c);
     uint64_t running = 0;
     // retire the slot's chunk: learn its packed size, start the payload copy at the running offset
     auto retire = [&](Slot& s) -> int {
@@ -608,9 +677,11 @@ int b200lz4_compress_fast_compact_host(const uint8_t* src_base, const uint64_t* 
     for (int k = 0; k < NSLOTS; k++) { rc = retire(c->slot[(cur + k) % NSLOTS]); if (rc) return rc; }
     for (int k = 0; k < NSLOTS; k++) { Slot& s = c->slot[k]; if (s.draining) { CK(cudaEventSynchronize(s.drained)); s.draining = false; } }
     if (total) *total = running;
+    guard.completed = true;
     return 0;
 }
 
+int b200lz4_context_count(void) { return g_contexts.load(std::memory_order_relaxed); }
 uint64_t b200lz4_launch_count(void) { return g_launches.load(std::memory_order_relaxed) + g_launch_count; }
 void     b200lz4_launch_count_reset(void) { g_launches.store(0, std::memory_order_relaxed); g_launch_count = 0; }
 

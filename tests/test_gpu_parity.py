@@ -1,6 +1,7 @@
 """GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same seeded
 inputs.  Decompression and hashes must be bit-exact (including negative return codes of the safe
 decoder); compression must emit a valid LZ4 block that the oracle decodes back to the input."""
+import os
 import random
 
 import numpy as np
@@ -321,6 +322,45 @@ def test_compact_host(b200, checker):
         pos += int(olen[k])
 
 
+def test_failed_pipeline_call_leaves_nothing_in_flight(b200):
+    """A host-buffer call that fails after some chunks were queued (here: `dst_capacity too small for the packed stream`,
+    found when the FIRST chunk retires while the next two are in flight) must drain them: the next call on the same
+    thread would otherwise retire the stale chunks into its own result / offset arrays.  Three chunks are needed: chunks
+    hold at most 65 536 blocks (tiny blocks reach that on a GPU), or B200LZ4_CHUNK_MB bytes (the emulator slice of
+    the CPU suite sets it to 1 and uses 4 KiB blocks, since every emulated CTA costs milliseconds)."""
+    chunk_mb = int(os.environ.get("B200LZ4_CHUNK_MB", "256"))
+    if chunk_mb <= 4:
+        bl = 4096; per_chunk = (chunk_mb << 20) // bl
+    else:
+        bl = 20; per_chunk = 65536
+    n = 2 * per_chunk + 100
+    cl = bl + 1 + (0 if bl < 15 else (bl - 15) // 255 + 1)                # random bytes: one literals-only sequence
+    hdr = cl - bl
+    rng = np.random.default_rng(77)
+    src = rng.integers(0, 256, n * bl, dtype=np.uint8)
+    soff, slen = b200.batch.uniform_layout(n, bl)
+    small = np.zeros(1000, dtype=np.uint8)
+    with pytest.raises(b200.B200Error, match="dst_capacity"):
+        b200.batch.compress_fast_compact_host(src, soff, slen, small, max_src_len=65536)
+    # same thread, same streams: a short batch and then the full one must come back exact
+    dst = np.zeros(n * cl + 64, dtype=np.uint8)
+    ooff, olen, total = b200.batch.compress_fast_compact_host(src[:5 * bl], soff[:5], slen[:5], dst, max_src_len=65536)
+    assert total == 5 * cl and (olen == cl).all() and (ooff == np.arange(5) * cl).all()
+    ooff, olen, total = b200.batch.compress_fast_compact_host(src, soff, slen, dst, max_src_len=65536)
+    assert total == n * cl and (olen == cl).all()
+    assert (ooff == np.arange(n, dtype=np.uint64) * np.uint64(cl)).all()
+    packed = dst[:total].reshape(n, cl)
+    assert (packed[:, 0] == (min(bl, 15) << 4)).all() and (packed[:, hdr:] == src.reshape(n, bl)).all()
+    # the slot-layout batch path after its own argument error (a dst slot out of order, found at the third chunk)
+    coff, ccap = b200.batch.uniform_layout(n, cl)
+    bad = coff.copy(); bad[2 * per_chunk + 50] = 0
+    comp = np.zeros(n * cl, dtype=np.uint8)
+    with pytest.raises(b200.B200Error, match="ascend"):
+        b200.batch.compress_fast_batch_host(src, soff, slen, comp, bad, ccap, max_src_len=65536)
+    clen = b200.batch.compress_fast_batch_host(src[:7 * bl], soff[:7], slen[:7], comp, coff[:7], ccap[:7], max_src_len=65536)
+    assert (clen == cl).all() and (comp[:7 * cl].reshape(7, cl)[:, hdr:] == src[:7 * bl].reshape(7, bl)).all()
+
+
 def test_xxhash_batches(b200, checker):
     rng = random.Random(5)
     bufs = [rng.randbytes(n) for n in list(range(0, 70)) + [255, 256, 257, 1000, 4096, 4097, 65536, 100001]]
@@ -621,3 +661,36 @@ def test_decompress_fast_does_not_walk_past_the_stream(b200, checker, decoder):
         assert res[k] == len(comp[k]), (decoder, k, int(res[k]), len(comp[k]))
         assert dst[int(doff[k]):int(doff[k]) + len(d)].tobytes() == d, (decoder, k)
         assert (dst[int(doff[k]) + len(d):int(doff[k]) + len(d) + 16] == 0x55).all(), (decoder, k)
+
+
+def test_contexts_are_reused_across_threads(b200, checker):
+    """LZ4Compressor instances are singletons used from any number of threads (LZ4Compressor.java:25): every thread gets
+    its own streams and staging, and a thread that exits hands them to the next new thread instead of leaking them."""
+    import threading
+    lib = b200._native.lib()
+    data = checker.datagen(3000, 0.5, 0.0, 9).tobytes()
+    comp = b200.LZ4Factory.b200Instance().fastCompressor().compress(data)        # this thread's context exists now
+    base = lib.b200lz4_context_count()
+    errs = []
+
+    def work(k):
+        try:
+            f = b200.LZ4Factory.b200Instance()
+            c = f.fastCompressor().compress(data)
+            assert c == comp
+            assert f.fastDecompressor().decompress(c, destLen=len(data)) == data
+            assert b200.XXHashFactory.b200Instance().hash64().hash(data, 0, len(data), k) == checker.xxh64(data, k)
+        except Exception as e:      # noqa: BLE001
+            errs.append(e)
+
+    import time
+    for k in range(8):                       # eight threads one after the other: they share one or two contexts
+        t = threading.Thread(target=work, args=(k,)); t.start(); t.join()
+        time.sleep(0.05)                     # join() returns before the OS thread has run its thread-exit hooks
+    assert not errs, errs
+    assert base + 1 <= lib.b200lz4_context_count() <= base + 3
+    ts = [threading.Thread(target=work, args=(k,)) for k in range(4)]    # four at once: at most four contexts alive
+    for t in ts: t.start()
+    for t in ts: t.join()
+    assert not errs, errs
+    assert lib.b200lz4_context_count() <= base + 3 + 4
