@@ -50,6 +50,10 @@ int         b200lz4_version(void);
 int         b200lz4_device_count(void);           /* >= 0, or B200LZ4_E_NODEVICE            */
 int         b200lz4_set_device(int device);       /* device used by the calling thread      */
 const char* b200lz4_last_error(void);             /* thread-local, never NULL                */
+/* The hash entry points return the hash VALUE (like XXH32/XXH64, xxhash.c:392,855), so they cannot return an error
+ * code: b200xxh32 / b200xxh64 / b200xxh*_digest clear this thread-local status on entry and leave a B200LZ4_E_* in it
+ * when they could not compute (they then return 0).  A binding must check it after each of those calls and throw. */
+int         b200lz4_last_status(void);
 /* Pin / unpin a caller-owned host range (e.g. a Java DirectByteBuffer) so the host batch
  * calls DMA straight from/to it.  Optional: unpinned memory works, slower. */
 int         b200lz4_host_register(void* p, size_t bytes);

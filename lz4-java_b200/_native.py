@@ -21,6 +21,7 @@ SYMBOLS = [
     ("b200lz4_device_count", _i, []),
     ("b200lz4_set_device", _i, [_i]),
     ("b200lz4_last_error", C.c_char_p, []),
+    ("b200lz4_last_status", _i, []),
     ("b200lz4_host_register", _i, [_vp, _sz]),
     ("b200lz4_host_unregister", _i, [_vp]),
     ("b200lz4_compressBound", _i, [_i]),
@@ -100,6 +101,14 @@ def check(rc: int) -> int:
     if rc in (E_NODEVICE, E_CUDA, E_ARG):
         raise B200Error(f"libb200lz4: {lib().b200lz4_last_error().decode()} (code {rc})")
     return rc
+
+
+def checked_value(v: int) -> int:
+    """for the entry points that return a hash value: raise if the call left an error status (see b200lz4_last_status)"""
+    rc = lib().b200lz4_last_status()
+    if rc:
+        raise B200Error(f"libb200lz4: {lib().b200lz4_last_error().decode()} (code {rc})")
+    return v
 
 
 def last_error() -> str:

@@ -18,16 +18,17 @@ namespace b200 {
 static std::atomic<unsigned long long> g_launches{0};
 unsigned long long g_launch_count = 0;      // launches made by frame.cu (single-threaded per call)
 static thread_local char tl_err[256] = "";
+static thread_local int tl_status = 0;          // B200LZ4_E_* of the last value-returning call (hashes, digests) on this thread
 static thread_local int tl_device = -1;          // -1: not chosen yet (defaults to device 0)
 
 static int fail_cuda(cudaError_t e, const char* where)
 {
     snprintf(tl_err, sizeof tl_err, "%s: %s", where, cudaGetErrorString(e));
     if (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver || e == cudaErrorInitializationError)
-        return B200LZ4_E_NODEVICE;
-    return B200LZ4_E_CUDA;
+        return tl_status = B200LZ4_E_NODEVICE;
+    return tl_status = B200LZ4_E_CUDA;
 }
-static int fail_arg(const char* what) { snprintf(tl_err, sizeof tl_err, "invalid argument: %s", what); return B200LZ4_E_ARG; }
+static int fail_arg(const char* what) { snprintf(tl_err, sizeof tl_err, "invalid argument: %s", what); return tl_status = B200LZ4_E_ARG; }
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail_cuda(e_, #call); } while (0)
 
 static int ensure_device()
@@ -35,7 +36,7 @@ static int ensure_device()
     int cnt = 0;
     cudaError_t e = cudaGetDeviceCount(&cnt);
     if (e != cudaSuccess) return fail_cuda(e, "cudaGetDeviceCount");
-    if (cnt <= 0) { snprintf(tl_err, sizeof tl_err, "no CUDA device"); return B200LZ4_E_NODEVICE; }
+    if (cnt <= 0) { snprintf(tl_err, sizeof tl_err, "no CUDA device"); return tl_status = B200LZ4_E_NODEVICE; }
     if (tl_device < 0) {
         // no b200lz4_set_device() on this thread yet: adopt the thread's CURRENT device (0 on a fresh thread) instead of
         // forcing device 0, so a caller that already selected a GPU (torch.cuda.set_device, cudaSetDevice) and hands
@@ -410,6 +411,7 @@ int b200lz4_set_device(int device)
 }
 
 const char* b200lz4_last_error(void) { return tl_err; }
+int b200lz4_last_status(void) { return tl_status; }
 
 int b200lz4_host_register(void* p, size_t bytes)
 {
@@ -459,6 +461,7 @@ int b200lz4_decompress_fast(const char* src, char* dst, int originalSize)
 uint32_t b200xxh32(const void* input, size_t len, uint32_t seed)
 {
     const uint64_t zero = 0; int32_t l = (int32_t)len; uint32_t out = 0; static const char dummy = 0;
+    tl_status = 0;
     if (len > 0x7FFFFFFFu) { fail_arg("len > 2^31-1"); return 0; }
     if (hash_host_batch<uint32_t>(32, (const uint8_t*)(input ? input : &dummy), &zero, &l, seed, &out, 1)) return 0;
     return out;
@@ -466,6 +469,7 @@ uint32_t b200xxh32(const void* input, size_t len, uint32_t seed)
 uint64_t b200xxh64(const void* input, size_t len, uint64_t seed)
 {
     const uint64_t zero = 0; int32_t l = (int32_t)len; uint64_t out = 0; static const char dummy = 0;
+    tl_status = 0;
     if (len > 0x7FFFFFFFu) { fail_arg("len > 2^31-1"); return 0; }
     if (hash_host_batch<uint64_t>(64, (const uint8_t*)(input ? input : &dummy), &zero, &l, seed, &out, 1)) return 0;
     return out;
@@ -518,7 +522,8 @@ static int stream_update(void* hv, const void* input, size_t len)
 }
 static uint64_t stream_digest(void* hv)
 {
-    StreamHandle* h = (StreamHandle*)hv; if (!h) return 0;
+    tl_status = 0;
+    StreamHandle* h = (StreamHandle*)hv; if (!h) { fail_arg("null state"); return 0; }
     cudaSetDevice(h->device);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     if (h->bits == 32) {

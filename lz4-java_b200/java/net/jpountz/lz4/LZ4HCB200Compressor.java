@@ -22,8 +22,11 @@ final class LZ4HCB200Compressor extends LZ4Compressor {
     checkRange(src, srcOff, srcLen);
     checkRange(dest, destOff, maxDestLen);
     final int result = LZ4B200JNI.LZ4_compressHC(src, null, srcOff, srcLen, dest, null, destOff, maxDestLen, compressionLevel);
+    if (result < -1000000) {
+      throw new LZ4Exception("B200 backend error " + result);   // B200LZ4_E_*: no device / CUDA error
+    }
     if (result <= 0) {
-      throw new LZ4Exception();
+      throw new LZ4Exception();                                 // LZ4HCJNICompressor.java:47-49
     }
     return result;
   }
@@ -42,8 +45,11 @@ final class LZ4HCB200Compressor extends LZ4Compressor {
     final int dof = destOff + (destArr != null ? dest.arrayOffset() : 0);
     final int result = LZ4B200JNI.LZ4_compressHC(srcArr, srcArr == null ? src : null, so, srcLen,
         destArr, destArr == null ? dest : null, dof, maxDestLen, compressionLevel);
+    if (result < -1000000) {
+      throw new LZ4Exception("B200 backend error " + result);   // B200LZ4_E_*: no device / CUDA error
+    }
     if (result <= 0) {
-      throw new LZ4Exception();
+      throw new LZ4Exception();                                 // LZ4HCJNICompressor.java:47-49
     }
     return result;
   }

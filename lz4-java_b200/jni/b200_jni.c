@@ -132,6 +132,16 @@ JNIEXPORT jint JNICALL Java_net_jpountz_lz4_LZ4B200JNI_registerDirectBuffer(JNIE
 /* ---------------------------------------------------------------- XXHash (reference: XXHashJNI.c:42-255) */
 JNIEXPORT void JNICALL Java_net_jpountz_xxhash_XXHashB200JNI_init(JNIEnv* env, jclass cls) { (void)env; (void)cls; }
 
+/* The hash calls return the hash value, so a backend failure (no device, CUDA error) cannot travel in the return
+ * value: it is thrown as java.lang.IllegalStateException carrying b200lz4_last_error() — never a silent 0. */
+static void throw_if_failed(JNIEnv* env)
+{
+    if (b200lz4_last_status() != 0) {
+        jclass ise = (*env)->FindClass(env, "java/lang/IllegalStateException");
+        if (ise != NULL) (*env)->ThrowNew(env, ise, b200lz4_last_error());
+    }
+}
+
 JNIEXPORT jint JNICALL Java_net_jpountz_xxhash_XXHashB200JNI_XXH32
   (JNIEnv* env, jclass cls, jbyteArray buf, jint off, jint len, jint seed)
 {
@@ -139,13 +149,17 @@ JNIEXPORT jint JNICALL Java_net_jpountz_xxhash_XXHashB200JNI_XXH32
     if (in == NULL) return 0;
     jint h = (jint)b200xxh32(in + off, (size_t)len, (uint32_t)seed);
     (*env)->ReleasePrimitiveArrayCritical(env, buf, in, JNI_ABORT);
+    throw_if_failed(env);
     return h;
 }
 JNIEXPORT jint JNICALL Java_net_jpountz_xxhash_XXHashB200JNI_XXH32BB
   (JNIEnv* env, jclass cls, jobject buf, jint off, jint len, jint seed)
 {
     char* in = (char*)(*env)->GetDirectBufferAddress(env, buf);
-    return in == NULL ? 0 : (jint)b200xxh32(in + off, (size_t)len, (uint32_t)seed);
+    if (in == NULL) return 0;
+    jint h = (jint)b200xxh32(in + off, (size_t)len, (uint32_t)seed);
+    throw_if_failed(env);
+    return h;
 }
 JNIEXPORT jlong JNICALL Java_net_jpountz_xxhash_XXHashB200JNI_XXH32_1init(JNIEnv* env, jclass cls, jint seed)
 { return (jlong)(intptr_t)b200xxh32_create((uint32_t)seed); }
@@ -154,11 +168,12 @@ JNIEXPORT void JNICALL Java_net_jpountz_xxhash_XXHashB200JNI_XXH32_1update
 {
     char* in = (char*)(*env)->GetPrimitiveArrayCritical(env, src, 0);
     if (in == NULL) return;
-    b200xxh32_update((void*)(intptr_t)state, in + off, (size_t)len);
+    int rc = b200xxh32_update((void*)(intptr_t)state, in + off, (size_t)len);
     (*env)->ReleasePrimitiveArrayCritical(env, src, in, JNI_ABORT);
+    if (rc != 0) throw_if_failed(env);
 }
 JNIEXPORT jint JNICALL Java_net_jpountz_xxhash_XXHashB200JNI_XXH32_1digest(JNIEnv* env, jclass cls, jlong state)
-{ return (jint)b200xxh32_digest((void*)(intptr_t)state); }
+{ jint h = (jint)b200xxh32_digest((void*)(intptr_t)state); throw_if_failed(env); return h; }
 JNIEXPORT void JNICALL Java_net_jpountz_xxhash_XXHashB200JNI_XXH32_1free(JNIEnv* env, jclass cls, jlong state)
 { b200xxh32_free((void*)(intptr_t)state); }
 
@@ -169,13 +184,17 @@ JNIEXPORT jlong JNICALL Java_net_jpountz_xxhash_XXHashB200JNI_XXH64
     if (in == NULL) return 0;
     jlong h = (jlong)b200xxh64(in + off, (size_t)len, (uint64_t)seed);
     (*env)->ReleasePrimitiveArrayCritical(env, buf, in, JNI_ABORT);
+    throw_if_failed(env);
     return h;
 }
 JNIEXPORT jlong JNICALL Java_net_jpountz_xxhash_XXHashB200JNI_XXH64BB
   (JNIEnv* env, jclass cls, jobject buf, jint off, jint len, jlong seed)
 {
     char* in = (char*)(*env)->GetDirectBufferAddress(env, buf);
-    return in == NULL ? 0 : (jlong)b200xxh64(in + off, (size_t)len, (uint64_t)seed);
+    if (in == NULL) return 0;
+    jlong h = (jlong)b200xxh64(in + off, (size_t)len, (uint64_t)seed);
+    throw_if_failed(env);
+    return h;
 }
 JNIEXPORT jlong JNICALL Java_net_jpountz_xxhash_XXHashB200JNI_XXH64_1init(JNIEnv* env, jclass cls, jlong seed)
 { return (jlong)(intptr_t)b200xxh64_create((uint64_t)seed); }
@@ -184,11 +203,12 @@ JNIEXPORT void JNICALL Java_net_jpountz_xxhash_XXHashB200JNI_XXH64_1update
 {
     char* in = (char*)(*env)->GetPrimitiveArrayCritical(env, src, 0);
     if (in == NULL) return;
-    b200xxh64_update((void*)(intptr_t)state, in + off, (size_t)len);
+    int rc = b200xxh64_update((void*)(intptr_t)state, in + off, (size_t)len);
     (*env)->ReleasePrimitiveArrayCritical(env, src, in, JNI_ABORT);
+    if (rc != 0) throw_if_failed(env);
 }
 JNIEXPORT jlong JNICALL Java_net_jpountz_xxhash_XXHashB200JNI_XXH64_1digest(JNIEnv* env, jclass cls, jlong state)
-{ return (jlong)b200xxh64_digest((void*)(intptr_t)state); }
+{ jlong h = (jlong)b200xxh64_digest((void*)(intptr_t)state); throw_if_failed(env); return h; }
 JNIEXPORT void JNICALL Java_net_jpountz_xxhash_XXHashB200JNI_XXH64_1free(JNIEnv* env, jclass cls, jlong state)
 { b200xxh64_free((void*)(intptr_t)state); }
 

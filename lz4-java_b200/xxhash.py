@@ -16,7 +16,7 @@ class XXHash32:
         if length is None:
             length = len(a) - off
         _check_range(a, off, length)
-        return N.lib().b200xxh32(_addr(a, off) if length else None, length, seed & 0xFFFFFFFF)
+        return N.checked_value(N.lib().b200xxh32(_addr(a, off) if length else None, length, seed & 0xFFFFFFFF))
 
 
 class XXHash64:
@@ -25,7 +25,7 @@ class XXHash64:
         if length is None:
             length = len(a) - off
         _check_range(a, off, length)
-        return N.lib().b200xxh64(_addr(a, off) if length else None, length, seed & 0xFFFFFFFFFFFFFFFF)
+        return N.checked_value(N.lib().b200xxh64(_addr(a, off) if length else None, length, seed & 0xFFFFFFFFFFFFFFFF))
 
 
 class _Streaming:
@@ -60,7 +60,7 @@ class _Streaming:
 
     def getValue(self) -> int:
         self._check()
-        return getattr(self._L, f"b200xxh{self._bits}_digest")(self._state)
+        return N.checked_value(getattr(self._L, f"b200xxh{self._bits}_digest")(self._state))
 
     def close(self):
         if self._state:

@@ -59,6 +59,13 @@ def test_no_device_is_loud(b200):
         b200.batch.xxh32_batch_host(src, [0], [100])
     with pytest.raises(b200.B200Error):
         b200.XXHashFactory.b200Instance()
+    # the hash calls return the VALUE: the failure travels in b200lz4_last_status(), and the mirror raises on it
+    assert lib.b200xxh32(src.ctypes.data, 100, 0) == 0 and lib.b200lz4_last_status() == b200._native.E_NODEVICE
+    assert lib.b200xxh64(src.ctypes.data, 100, 0) == 0 and lib.b200lz4_last_status() == b200._native.E_NODEVICE
+    with pytest.raises(b200.B200Error):
+        b200.xxhash.XXHash32().hash(src.tobytes(), 0, 100, 0)
+    with pytest.raises(b200.B200Error):
+        b200.xxhash.XXHash64().hash(src.tobytes(), 0, 100, 0)
 
 
 def test_product_does_not_import_oracle():
