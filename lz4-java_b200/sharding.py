@@ -36,3 +36,57 @@ def max_over_ranks(seconds: float, group=None) -> float:
     t = torch.tensor([seconds], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
     return float(t.item())
+
+
+def frame_boundaries(buf) -> list[tuple[int, int]]:
+    """[(start, end)) of every frame (skippable frames included) in a buffer of concatenated LZ4 frames — the walk
+    LZ4FrameInputStream.nextFrameInfo / readHeader / readBlock make (LZ4FrameInputStream.java:132-321), sizes only:
+    no payload byte is read, no checksum verified (the decoder does that).  Sharding metadata, not a codec: a frame's
+    content checksum chains over all its blocks (`:264-273`), so config 3 is split across GPUs BY FRAME, never by block."""
+    b = memoryview(buf).cast("B")
+    n, ip, out = len(b), 0, []
+
+    def le32(p):
+        if n - p < 4:
+            raise EOFError("Stream ended prematurely")
+        return b[p] | (b[p + 1] << 8) | (b[p + 2] << 16) | (b[p + 3] << 24)
+
+    while ip < n:
+        start = ip
+        magic = le32(ip); ip += 4
+        if (magic >> 4) == (0x184D2A50 >> 4):                     # skippable frame: 4-byte size, payload
+            ip += 4 + le32(ip)
+        elif magic == 0x184D2204:
+            if n - ip < 3:
+                raise EOFError("Stream ended prematurely")
+            flg = b[ip]
+            ip += 2 + (8 if flg & 8 else 0) + 1                   # FLG, BD, [content size], HC
+            while True:
+                word = le32(ip); ip += 4
+                size = word & 0x7FFFFFFF
+                if size == 0:
+                    break                                         # EndMark
+                ip += size + (4 if flg & 0x10 else 0)             # payload, [block checksum]
+            if flg & 4:
+                ip += 4                                           # content checksum
+        else:
+            raise IOError("Stream unsupported (invalid magic bytes)")
+        if ip > n:
+            raise EOFError("Stream ended prematurely")
+        out.append((start, ip))
+    return out
+
+
+def shard_frames(sizes, world: int) -> list[tuple[int, int]]:
+    """Contiguous frame ranges [lo, hi) for ranks 0..world-1, balanced by BYTES (frames differ in size, so an equal
+    frame count can leave one GPU with most of the work): rank r's range ends at the first frame boundary at or past
+    r+1 shares of the total.  Every frame lands on exactly one rank; trailing ranks may be empty when frames are few."""
+    total = sum(sizes)
+    cuts, acc, k = [0], 0, 0
+    for r in range(1, world):
+        target = total * r / world
+        while k < len(sizes) and acc + sizes[k] / 2 <= target:    # a frame goes to the side its midpoint is on
+            acc += sizes[k]; k += 1
+        cuts.append(k)
+    cuts.append(len(sizes))
+    return [(cuts[r], cuts[r + 1]) for r in range(world)]

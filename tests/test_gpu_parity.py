@@ -694,3 +694,24 @@ def test_contexts_are_reused_across_threads(b200, checker):
     for t in ts: t.join()
     assert not errs, errs
     assert lib.b200lz4_context_count() <= base + 3 + 4
+
+
+def test_frames_sharded_by_frame(b200, port):
+    """config 3's multi-GPU split: every rank decodes its own byte-balanced range of whole frames (here the ranks run one
+    after the other on one GPU); the pieces concatenate to the single-rank result"""
+    from lz4java_b200.sharding import frame_boundaries, shard_frames
+    frames, plain = [], []
+    for k in range(12):
+        d = port.datagen(50000 + 40000 * (k % 4), 0.5, 0.0, 20 + k).tobytes()
+        frames.append(port.frame_compress(d, 4 + k % 2, 1 + 2 * (k % 2))); plain.append(d)
+    stream = b"".join(frames)
+    whole = b200.decompress_frames(stream, sum(map(len, plain)))
+    assert whole == b"".join(plain)
+    bounds = frame_boundaries(stream)
+    assert len(bounds) == len(frames)
+    for world in (2, 8):
+        got = b""
+        for lo, hi in shard_frames([e - s for s, e in bounds], world):
+            if hi > lo:
+                got += b200.decompress_frames(stream[bounds[lo][0]:bounds[hi - 1][1]], sum(map(len, plain[lo:hi])))
+        assert got == whole

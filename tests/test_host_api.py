@@ -59,3 +59,43 @@ def test_shard_ranges_cover_and_ascend(b200):
                 assert b == c and a <= b and c <= d
             sizes = [b - a for a, b in pieces]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_frame_boundaries_and_byte_balanced_frame_shards(port):
+    """config 3 shards BY FRAME (a content checksum chains over a frame's blocks): the boundary walk finds every frame
+    of a concatenated stream whatever its flags, and the ranges handed to the ranks cover each frame once, balanced by
+    bytes; each rank's slice decodes (CPU checker here) to exactly its part of the whole"""
+    from lz4java_b200.sharding import frame_boundaries, shard_frames
+    import random
+    rng = random.Random(11)
+    skip = bytes([0x53, 0x2A, 0x4D, 0x18, 5, 0, 0, 0, 9, 8, 7, 6, 5])
+    parts, plain = [], []
+    for k in range(23):
+        n = rng.choice([0, 1, 100, 65536, 70000, 300000])
+        d = port.datagen(n, 0.5, 0.0, k).tobytes() if k % 5 else rng.randbytes(n)      # some frames hold stored blocks
+        parts.append(port.frame_compress(d, rng.choice([4, 5, 7]), rng.choice([0, 1, 3, 5, 7]))); plain.append(d)
+        if k % 7 == 3:
+            parts.append(skip); plain.append(b"")
+    stream = b"".join(parts)
+    bounds = frame_boundaries(stream)
+    assert [e - s for s, e in bounds] == [len(p) for p in parts] and bounds[0][0] == 0 and bounds[-1][1] == len(stream)
+    sizes = [e - s for s, e in bounds]
+    for world in (1, 2, 3, 8, 64):
+        ranges = shard_frames(sizes, world)
+        assert len(ranges) == world and ranges[0][0] == 0 and ranges[-1][1] == len(sizes)
+        assert all(ranges[r][1] == ranges[r + 1][0] for r in range(world - 1))
+        got = b""
+        for lo, hi in ranges:
+            if hi > lo:
+                piece = stream[bounds[lo][0]:bounds[hi - 1][1]]
+                want = b"".join(plain[lo:hi])
+                r, out = port.frame_decompress(piece, len(want) + 8)
+                assert r == len(want) and out == want
+                got += out
+        assert got == b"".join(plain)
+        if world <= 3:                                            # balanced: no rank above its share by more than one frame
+            share = len(stream) / world
+            assert max(sum(sizes[lo:hi]) for lo, hi in ranges) <= share + max(sizes)
+    for bad in (stream[:-3], b"\x01\x02\x03\x04" + stream, stream[:bounds[2][0] + 5]):
+        with pytest.raises((EOFError, IOError)):
+            frame_boundaries(bad)
