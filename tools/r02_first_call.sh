@@ -1,0 +1,22 @@
+#!/bin/bash
+# First GPU-box visit of round 2 (round 1 ended with its GPU budget spent, so everything written after the last
+# measurement is queued here):
+#   /usr/local/graft/bin/gpurun --timeout 2400 -- 'bash tools/r02_first_call.sh'
+# 1. the GPU parity suite (incl. the regression tests that have only run on the CPU emulator so far: fast-decoder
+#    stream end, failed-pipeline drain, context reuse across threads, frames sharded by frame)
+# 2. both bench arms on the current build -> the round's first BENCH line
+# 3. the unmeasured second HC design (B200_EXPERIMENTAL: config 4 with b200lz4_hc_algo = 2) next to the default
+# 4. end-to-end chunk-size sweep of the host pipeline (B200LZ4_CHUNK_MB)
+# 5. launch list under ncu for the bench command
+# Outputs under gpurun_out/r02a/ (copy what is to be judged into profiles/).
+ulimit -c 0
+O=gpurun_out/r02a; mkdir -p $O
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > $O/gpu.txt 2>&1
+timeout 1200 python -m pytest tests -m gpu -q -W ignore::DeprecationWarning > $O/gpu_tests.log 2>&1; tail -3 $O/gpu_tests.log | cut -c1-300
+B200_EXPERIMENTAL=1 timeout 600 python -m pytest tests -m gpu -q -W ignore::DeprecationWarning -k "hc" > $O/gpu_tests_experimental.log 2>&1; tail -2 $O/gpu_tests_experimental.log | cut -c1-300
+timeout 900 python bench.py --impl reference > $O/bench_reference_arm.json 2> $O/bench_reference.err; tail -c 300 $O/bench_reference_arm.json
+timeout 1500 python bench.py > $O/bench_full.json 2> $O/bench_full.err; tail -c 600 $O/bench_full.json
+B200_EXPERIMENTAL=1 timeout 1500 python tools/bench_configs.py > $O/secondary_configs.log 2>&1; tail -12 $O/secondary_configs.log | cut -c1-300
+for mb in 64 128 512; do B200LZ4_CHUNK_MB=$mb timeout 300 python tools/e2e_probe.py 2>&1 | head -3 | cut -c1-300; done > $O/e2e_chunk_sweep.log 2>&1; cat $O/e2e_chunk_sweep.log
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/bench_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu > $O/bench_under_ncu.log 2>&1
+ls -la $O
