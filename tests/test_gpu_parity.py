@@ -715,3 +715,85 @@ def test_frames_sharded_by_frame(b200, port):
             if hi > lo:
                 got += b200.decompress_frames(stream[bounds[lo][0]:bounds[hi - 1][1]], sum(map(len, plain[lo:hi])))
         assert got == whole
+
+
+def _golden(name):
+    import json
+    return json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name)))
+
+
+def test_golden_vectors_on_gpu(b200, port, decoder):
+    """The CUDA path against the COMMITTED outputs of the reference's own C (tests/golden/kat.json, generated from
+    oracle/_ref by make_golden.py): XXH32/XXH64 values, the safe decoder's return code on every malformed vector x
+    capacity, the fast decoder's, and — for every corpus block — decoding the stream whose digest the fixture records."""
+    import hashlib
+    kat = _golden("kat.json")
+    stream = port.datagen(200000, 0.5, 0.0, 77)
+    # hashes: one batch per seed over the prefixes
+    for seed in (0, 0x9747B28C):
+        ents = [e for e in kat["xxh"] if e["seed"] == seed]
+        off = np.zeros(len(ents), dtype=np.uint64)
+        ln = np.array([e["len"] for e in ents], dtype=np.int32)
+        h32 = b200.batch.xxh32_batch_host(stream, off, ln, seed)
+        h64 = b200.batch.xxh64_batch_host(stream, off, ln, seed * 0x100000001)
+        for k, e in enumerate(ents):
+            assert int(h32[k]) == e["xxh32"] and int(h64[k]) == e["xxh64"], e
+    # malformed vectors: return codes recorded from the reference
+    ms = kat["malformed_safe"]
+    src, soff, slen = corpus.pack([bytes.fromhex(e["hex"]) for e in ms], pad=8)
+    doff, dcap, total = _slots([e["cap"] for e in ms])
+    res = b200.batch.decompress_safe_batch_host(src, soff, slen, np.zeros(total, dtype=np.uint8), doff, dcap)
+    for k, e in enumerate(ms):
+        assert int(res[k]) == e["ret"], e
+    mf = kat["malformed_fast"]
+    padded = [bytes.fromhex(e["hex"]) + bytes(e["n"] + 64) for e in mf]
+    src, soff, slen = corpus.pack(padded)
+    doff, dlen, total = _slots([e["n"] for e in mf])
+    res = b200.batch.decompress_fast_batch_host(src, soff, slen, np.zeros(total, dtype=np.uint8), doff, dlen)
+    for k, e in enumerate(mf):
+        assert int(res[k]) == e["ret"], e
+    # corpus blocks: the pinned restatement reproduces the reference's stream (digest in the fixture); the GPU decodes it
+    items = corpus.blocks(port)
+    assert [n for n, _ in items] == [e["name"] for e in kat["compress"]]
+    comp = [port.compress(d) for _, d in items]
+    for c, (_, d), e in zip(comp, items, kat["compress"]):
+        assert hashlib.sha256(c).hexdigest() == e["c_sha256"] and hashlib.sha256(bytes(d)).hexdigest() == e["in_sha256"]
+    src, soff, slen = corpus.pack(comp)
+    doff, dcap, total = _slots([len(d) for _, d in items])
+    dst = np.zeros(total, dtype=np.uint8)
+    res = b200.batch.decompress_safe_batch_host(src, soff, slen, dst, doff, dcap)
+    for k, e in enumerate(kat["compress"]):
+        assert int(res[k]) == e["len"], e["name"]
+        assert hashlib.sha256(dst[int(doff[k]):int(doff[k]) + e["len"]].tobytes()).hexdigest() == e["in_sha256"], e["name"]
+
+
+def test_golden_calgary_on_gpu(b200, port, decoder):
+    """real data that travels to the GPU box: the reference's fast and HC-9 streams of Calgary cuts decode on the GPU
+    (safe and fast decoders) to bytes with the recorded digest; the GPU's own fast and HC streams of those bytes decode
+    back under the CPU checker, and the GPU HC stream is smaller than the reference's FAST stream"""
+    import base64
+    import hashlib
+    cal = _golden("calgary_lz4.json")["blocks"]
+    for key in ("fast_b64", "hc9_b64"):
+        comp = [base64.b64decode(b[key]) for b in cal]
+        src, soff, slen = corpus.pack([c + bytes(64) for c in comp])
+        slen_exact = np.array([len(c) for c in comp], dtype=np.int32)
+        doff, dcap, total = _slots([b["len"] for b in cal])
+        dst = np.zeros(total, dtype=np.uint8)
+        res = b200.batch.decompress_safe_batch_host(src, soff, slen_exact, dst, doff, dcap)
+        dst2 = np.zeros(total, dtype=np.uint8)
+        res2 = b200.batch.decompress_fast_batch_host(src, soff, slen, dst2, doff, dcap)
+        for k, b in enumerate(cal):
+            assert int(res[k]) == b["len"] and int(res2[k]) == len(comp[k]), (key, b["name"])
+            for out in (dst, dst2):
+                assert hashlib.sha256(out[int(doff[k]):int(doff[k]) + b["len"]].tobytes()).hexdigest() == b["sha256"], (key, b["name"])
+    if decoder != "batched":
+        return
+    plain = [dst[int(doff[k]):int(doff[k]) + b["len"]].tobytes() for k, b in enumerate(cal)]
+    f = b200.LZ4Factory.b200Instance()
+    for b, d in zip(cal, plain):
+        c = f.fastCompressor().compress(d)
+        assert port.decompress_safe(c, len(d)) == (len(d), d), b["name"]
+        h = f.highCompressor(9).compress(d)
+        assert port.decompress_safe(h, len(d)) == (len(d), d), b["name"]
+        assert len(h) < len(base64.b64decode(b["fast_b64"])), (b["name"], len(h))
