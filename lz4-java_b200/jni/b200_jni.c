@@ -163,6 +163,8 @@ JNIEXPORT jint JNICALL Java_net_jpountz_xxhash_XXHashB200JNI_XXH32BB
 }
 JNIEXPORT jlong JNICALL Java_net_jpountz_xxhash_XXHashB200JNI_XXH32_1init(JNIEnv* env, jclass cls, jint seed)
 { return (jlong)(intptr_t)b200xxh32_create((uint32_t)seed); }
+JNIEXPORT void JNICALL Java_net_jpountz_xxhash_XXHashB200JNI_XXH32_1reset(JNIEnv* env, jclass cls, jlong state, jint seed)
+{ b200xxh32_reset((void*)(intptr_t)state, (uint32_t)seed); }
 JNIEXPORT void JNICALL Java_net_jpountz_xxhash_XXHashB200JNI_XXH32_1update
   (JNIEnv* env, jclass cls, jlong state, jbyteArray src, jint off, jint len)
 {
@@ -198,6 +200,8 @@ JNIEXPORT jlong JNICALL Java_net_jpountz_xxhash_XXHashB200JNI_XXH64BB
 }
 JNIEXPORT jlong JNICALL Java_net_jpountz_xxhash_XXHashB200JNI_XXH64_1init(JNIEnv* env, jclass cls, jlong seed)
 { return (jlong)(intptr_t)b200xxh64_create((uint64_t)seed); }
+JNIEXPORT void JNICALL Java_net_jpountz_xxhash_XXHashB200JNI_XXH64_1reset(JNIEnv* env, jclass cls, jlong state, jlong seed)
+{ b200xxh64_reset((void*)(intptr_t)state, (uint64_t)seed); }
 JNIEXPORT void JNICALL Java_net_jpountz_xxhash_XXHashB200JNI_XXH64_1update
   (JNIEnv* env, jclass cls, jlong state, jbyteArray src, jint off, jint len)
 {

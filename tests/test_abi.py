@@ -88,3 +88,22 @@ def test_product_loader_has_no_library_switch(b200, monkeypatch):
             assert "os.environ" not in txt and "getenv" not in txt, f
     if not os.environ.get("B200LZ4_TEST_SO"):
         assert os.path.samefile(b200._native.SO_PATH, os.path.join(pkg, "libb200lz4.so"))
+
+
+def test_java_natives_have_shim_symbols_and_shim_calls_are_in_the_header():
+    """No JDK here, so the three layers are checked textually: every `native` method of the two Java JNI enums has its
+    Java_<class>_<method> definition in jni/b200_jni.c (JNI name mangling: '_' -> '_1'), and every b200* function the shim
+    calls is declared in include/b200lz4.h"""
+    shim = open(os.path.join(ROOT, "lz4-java_b200", "jni", "b200_jni.c")).read()
+    java = os.path.join(ROOT, "lz4-java_b200", "java", "net", "jpountz")
+    n = 0
+    for rel, cls in (("lz4/LZ4B200JNI.java", "net_jpountz_lz4_LZ4B200JNI"), ("xxhash/XXHashB200JNI.java", "net_jpountz_xxhash_XXHashB200JNI")):
+        for m in re.findall(r"native\s+\w+\s+(\w+)\(", open(os.path.join(java, rel)).read()):
+            assert re.search(r"\bJava_" + cls + "_" + m.replace("_", "_1") + r"\b", shim), (rel, m)
+            n += 1
+    assert n >= 27
+    defined = set(re.findall(r"\bJava_(\w+)\b", shim))
+    assert len(defined) == n, "a Java_ symbol in the shim has no native declaration"
+    declared = set(header_functions())
+    for call in set(re.findall(r"\b(b200(?:lz4|xxh(?:32|64))_?\w*)\s*\(", shim)):
+        assert call in declared, call
