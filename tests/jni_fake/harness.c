@@ -23,6 +23,7 @@ jint Java_net_jpountz_lz4_LZ4B200JNI_LZ4_1compressBound(JNIEnv*, jclass, jint);
 jint Java_net_jpountz_xxhash_XXHashB200JNI_XXH32(JNIEnv*, jclass, jbyteArray, jint, jint, jint);
 jlong Java_net_jpountz_xxhash_XXHashB200JNI_XXH64BB(JNIEnv*, jclass, jobject, jint, jint, jlong);
 jlong Java_net_jpountz_xxhash_XXHashB200JNI_XXH64_1init(JNIEnv*, jclass, jlong);
+void Java_net_jpountz_xxhash_XXHashB200JNI_XXH64_1reset(JNIEnv*, jclass, jlong, jlong);
 void Java_net_jpountz_xxhash_XXHashB200JNI_XXH64_1update(JNIEnv*, jclass, jlong, jbyteArray, jint, jint);
 jlong Java_net_jpountz_xxhash_XXHashB200JNI_XXH64_1digest(JNIEnv*, jclass, jlong);
 void Java_net_jpountz_xxhash_XXHashB200JNI_XXH64_1free(JNIEnv*, jclass, jlong);
@@ -54,6 +55,11 @@ int main(void)
     Java_net_jpountz_xxhash_XXHashB200JNI_XXH64_1update(env, NULL, st, &a_raw, OFF, 1234);
     Java_net_jpountz_xxhash_XXHashB200JNI_XXH64_1update(env, NULL, st, &a_raw, OFF + 1234, N - 1234);
     jlong hs = Java_net_jpountz_xxhash_XXHashB200JNI_XXH64_1digest(env, NULL, st);
+    /* getValue() is idempotent, and reset() re-seeds the SAME device state in place (B200StreamState.reset) */
+    if (Java_net_jpountz_xxhash_XXHashB200JNI_XXH64_1digest(env, NULL, st) != hs) { printf("digest not idempotent\n"); return 1; }
+    Java_net_jpountz_xxhash_XXHashB200JNI_XXH64_1reset(env, NULL, st, 42);
+    Java_net_jpountz_xxhash_XXHashB200JNI_XXH64_1update(env, NULL, st, &a_raw, OFF, N);
+    if (Java_net_jpountz_xxhash_XXHashB200JNI_XXH64_1digest(env, NULL, st) != hs) { printf("reset + update differs\n"); return 1; }
     Java_net_jpountz_xxhash_XXHashB200JNI_XXH64_1free(env, NULL, st);
     if (h64 != hs) { printf("xxh64 %llx != %llx\n", (long long)h64, (long long)hs); return 1; }
     jint h32 = Java_net_jpountz_xxhash_XXHashB200JNI_XXH32(env, NULL, &a_raw, OFF, N, 7);

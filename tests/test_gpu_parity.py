@@ -473,9 +473,10 @@ def test_jni_shim_through_fake_jnienv(b200, checker, tmp_path):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     exe = str(tmp_path / "jni_harness")
     pkg = os.path.join(root, "lz4-java_b200")
+    so = os.path.abspath(b200._native.SO_PATH)             # the library under test (libb200lz4.so unless the harness switched it)
     subprocess.run(["gcc", "-O1", "-I" + os.path.join(root, "tests", "jni_fake"), "-I" + os.path.join(root, "include"),
                     os.path.join(root, "tests", "jni_fake", "harness.c"), os.path.join(pkg, "jni", "b200_jni.c"),
-                    "-L" + pkg, "-lb200lz4", "-Wl,-rpath," + pkg, "-o", exe], check=True)
+                    so, "-Wl,-rpath," + os.path.dirname(so), "-o", exe], check=True)
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0 and out.stdout.startswith("ok"), out.stdout + out.stderr
     # the hashes printed by the harness must be the oracle's for the same generated bytes
