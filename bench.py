@@ -138,6 +138,27 @@ def thread_candidates():
     return sorted(c, reverse=True)
 
 
+def host_memory_budget():
+    """bytes of host memory this container may still use: min(cgroup limit - usage, MemAvailable); None if unknown"""
+    avail = None
+    try:
+        for line in open("/proc/meminfo"):
+            if line.startswith("MemAvailable:"):
+                avail = int(line.split()[1]) * 1024
+    except Exception:
+        pass
+    for lim_p, use_p in (("/sys/fs/cgroup/memory.max", "/sys/fs/cgroup/memory.current"),
+                         ("/sys/fs/cgroup/memory/memory.limit_in_bytes", "/sys/fs/cgroup/memory/memory.usage_in_bytes")):
+        try:
+            lim = open(lim_p).read().strip()
+            if lim != "max" and int(lim) < (1 << 60):
+                room = int(lim) - int(open(use_p).read().strip())
+                avail = room if avail is None else min(avail, room)
+        except Exception:
+            pass
+    return avail
+
+
 def cpu_roundtrip(chk, data, nblocks, threads, passes=3):
     """compress + fast-decompress `nblocks` blocks on `threads` host threads with the CPU library.
     Returns dict with GiB/s for each half, the round trip, and the ratio."""
@@ -391,8 +412,20 @@ def run_e2e(args, L, dev, host, rank, world):
     import torch.distributed as dist
     B = L.batch
     n = min(args.e2e_blocks, args.blocks)
-    nbytes = n * BLOCK
     bound = L.max_compressed_length(BLOCK)
+    # the e2e leg pins 2 x 64 KiB + 2 x bound bytes of host memory per block and per rank: keep all ranks of this node
+    # together under 40 % of what the container may still use (an 8-rank run must not drive the box out of memory)
+    room = host_memory_budget()
+    if room is not None:
+        local_world = env_int("LOCAL_WORLD_SIZE", world)
+        fit = int(0.4 * room / max(1, local_world) / (2 * BLOCK + 2 * bound))
+        if fit < n:
+            n = max(4096, fit // 4096 * 4096)
+    if world > 1:                                   # every rank runs the same sample size
+        nn = torch.tensor([n], device=dev, dtype=torch.int64)
+        dist.all_reduce(nn, op=dist.ReduceOp.MIN)
+        n = int(nn.item())
+    nbytes = n * BLOCK
     src_t = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
     comp_t = [torch.empty(n * bound, dtype=torch.uint8).pin_memory() for _ in range(2)]     # double-buffered between the threads
     out_t = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
