@@ -145,6 +145,27 @@ int b200lz4_compress_fast_compact_host(const uint8_t* src_base, const uint64_t* 
                                        uint8_t* dst_base, size_t dst_capacity, uint64_t* out_off,
                                        int32_t* result, size_t n, int max_src_len, uint64_t* total);
 
+/* ---------------------------------------------------------------- host batches, range-sharded over several GPUs
+ * ONE call from ONE process (a JVM) drives `ndev` GPUs: GPU devices[g] takes the contiguous block range
+ * [g*n/ndev, (g+1)*n/ndev) (sizes differ by at most one block) and runs the host pipeline above on its own streams
+ * from its own worker thread; blocks are independent, so there is no exchange between the GPUs and no collective
+ * (SURVEY.md 8e).  `devices` = NULL means devices 0..ndev-1.  Same layout rules and results as the single-GPU calls
+ * (result[] / out[] are filled for all n blocks; byte-identical output whatever ndev is).  Returns 0, or the first
+ * B200LZ4_E_* any shard reported (b200lz4_last_error() then names the device). */
+int b200lz4_compress_fast_batch_host_multi(const uint8_t* src_base, const uint64_t* src_off, const int32_t* src_len,
+                                           uint8_t* dst_base, const uint64_t* dst_off, const int32_t* dst_cap,
+                                           int32_t* result, size_t n, int max_src_len, const int* devices, int ndev);
+int b200lz4_decompress_safe_batch_host_multi(const uint8_t* src_base, const uint64_t* src_off, const int32_t* src_len,
+                                             uint8_t* dst_base, const uint64_t* dst_off, const int32_t* dst_cap,
+                                             int32_t* result, size_t n, const int* devices, int ndev);
+int b200lz4_decompress_fast_batch_host_multi(const uint8_t* src_base, const uint64_t* src_off, const int32_t* src_avail,
+                                             uint8_t* dst_base, const uint64_t* dst_off, const int32_t* dst_len,
+                                             int32_t* result, size_t n, const int* devices, int ndev);
+int b200xxh32_batch_host_multi(const uint8_t* base, const uint64_t* off, const int32_t* len, uint32_t seed,
+                               uint32_t* out, size_t n, const int* devices, int ndev);
+int b200xxh64_batch_host_multi(const uint8_t* base, const uint64_t* off, const int32_t* len, uint64_t seed,
+                               uint64_t* out, size_t n, const int* devices, int ndev);
+
 /* ---------------------------------------------------------------- LZ4 Frame batch decoder
  * LZ4FrameInputStream semantics (src/java/net/jpountz/lz4/LZ4FrameInputStream.java:132-321) over a buffer
  * of concatenated frames: the host indexes the container, the device verifies header/block/content

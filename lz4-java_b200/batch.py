@@ -87,6 +87,60 @@ def xxh64_batch_host(buf, off, length, seed=0) -> np.ndarray:
     return out
 
 
+# ------------------------------------------------------------------ host buffers, one process driving several GPUs
+def _devs(devices):
+    """devices: an int (0..k-1) or an explicit list of device indices -> (ctypes int array or None, count)"""
+    import ctypes
+    if isinstance(devices, int):
+        return None, devices
+    arr = (ctypes.c_int * len(devices))(*devices)
+    return arr, len(devices)
+
+
+def compress_fast_batch_host_multi(src, src_off, src_len, dst, dst_off, dst_cap, devices, max_src_len=0) -> np.ndarray:
+    """range-shards the batch over `devices` inside this process (b200lz4_compress_fast_batch_host_multi)"""
+    src_off, src_len, dst_off, dst_cap = _np(src_off, np.uint64), _np(src_len, np.int32), _np(dst_off, np.uint64), _np(dst_cap, np.int32)
+    res = np.zeros(len(src_off), dtype=np.int32)
+    arr, k = _devs(devices)
+    N.check(N.lib().b200lz4_compress_fast_batch_host_multi(_p(src), _p(src_off), _p(src_len), _p(dst), _p(dst_off), _p(dst_cap),
+                                                           _p(res), len(src_off), max_src_len, arr, k))
+    return res
+
+
+def decompress_safe_batch_host_multi(src, src_off, src_len, dst, dst_off, dst_cap, devices) -> np.ndarray:
+    src_off, src_len, dst_off, dst_cap = _np(src_off, np.uint64), _np(src_len, np.int32), _np(dst_off, np.uint64), _np(dst_cap, np.int32)
+    res = np.zeros(len(src_off), dtype=np.int32)
+    arr, k = _devs(devices)
+    N.check(N.lib().b200lz4_decompress_safe_batch_host_multi(_p(src), _p(src_off), _p(src_len), _p(dst), _p(dst_off), _p(dst_cap),
+                                                             _p(res), len(src_off), arr, k))
+    return res
+
+
+def decompress_fast_batch_host_multi(src, src_off, src_avail, dst, dst_off, dst_len, devices) -> np.ndarray:
+    src_off, src_avail, dst_off, dst_len = _np(src_off, np.uint64), _np(src_avail, np.int32), _np(dst_off, np.uint64), _np(dst_len, np.int32)
+    res = np.zeros(len(src_off), dtype=np.int32)
+    arr, k = _devs(devices)
+    N.check(N.lib().b200lz4_decompress_fast_batch_host_multi(_p(src), _p(src_off), _p(src_avail), _p(dst), _p(dst_off), _p(dst_len),
+                                                             _p(res), len(src_off), arr, k))
+    return res
+
+
+def xxh32_batch_host_multi(buf, off, length, devices, seed=0) -> np.ndarray:
+    off, length = _np(off, np.uint64), _np(length, np.int32)
+    out = np.zeros(len(off), dtype=np.uint32)
+    arr, k = _devs(devices)
+    N.check(N.lib().b200xxh32_batch_host_multi(_p(buf), _p(off), _p(length), seed & 0xFFFFFFFF, _p(out), len(off), arr, k))
+    return out
+
+
+def xxh64_batch_host_multi(buf, off, length, devices, seed=0) -> np.ndarray:
+    off, length = _np(off, np.uint64), _np(length, np.int32)
+    out = np.zeros(len(off), dtype=np.uint64)
+    arr, k = _devs(devices)
+    N.check(N.lib().b200xxh64_batch_host_multi(_p(buf), _p(off), _p(length), seed & 0xFFFFFFFFFFFFFFFF, _p(out), len(off), arr, k))
+    return out
+
+
 # ------------------------------------------------------------------ device-resident (torch tensors)
 def _stream_ptr():
     import torch

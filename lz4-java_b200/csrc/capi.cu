@@ -11,6 +11,8 @@
 #include <cstring>
 #include <mutex>
 #include <new>
+#include <string>
+#include <thread>
 #include <vector>
 
 namespace b200 {
@@ -384,6 +386,60 @@ static int one_block(Op op, const char* src, int src_len, char* dst, int dst_cap
     return res;
 }
 
+// ---- one process, several GPUs: contiguous block ranges, one worker thread (own device, own context) per GPU
+template <class ShardFn>
+static int run_sharded(size_t n, const int* devices, int ndev, ShardFn shard)
+{
+    if (ndev < 1 || ndev > 64) return fail_arg("ndev must be 1..64");
+    int cnt = b200lz4_device_count();
+    if (cnt < 0) return cnt;
+    for (int g = 0; g < ndev; g++) {
+        const int d = devices ? devices[g] : g;
+        if (d < 0 || d >= cnt) return fail_arg("device index in devices[]");
+    }
+    std::vector<int> rc((size_t)ndev, 0);
+    std::vector<std::string> msg((size_t)ndev);
+    std::vector<std::thread> th;
+    auto body = [&](int g) {
+        const size_t lo = n * (size_t)g / (size_t)ndev, hi = n * (size_t)(g + 1) / (size_t)ndev;
+        if (hi == lo) return;
+        int r = b200lz4_set_device(devices ? devices[g] : g);       // thread-local: this worker's device
+        if (r == 0) r = shard(lo, hi - lo);
+        rc[(size_t)g] = r;
+        if (r) msg[(size_t)g] = tl_err;
+    };
+    try {
+        for (int g = 1; g < ndev; g++) th.emplace_back(body, g);
+    } catch (...) {
+        for (auto& t : th) t.join();
+        return fail_arg("cannot start a worker thread");
+    }
+    const int my_device = tl_device;
+    int my_cuda_device = -1;
+    if (cudaGetDevice(&my_cuda_device) != cudaSuccess) my_cuda_device = -1;
+    body(0);                                                        // shard 0 runs on the calling thread
+    for (auto& t : th) t.join();
+    tl_device = my_device;                                          // the caller keeps its device, in the library and in CUDA
+    if (my_cuda_device >= 0) cudaSetDevice(my_cuda_device);
+    for (int g = 0; g < ndev; g++)
+        if (rc[(size_t)g]) {
+            snprintf(tl_err, sizeof tl_err, "device %d: %s", devices ? devices[g] : g, msg[(size_t)g].c_str());
+            return tl_status = rc[(size_t)g];
+        }
+    return 0;
+}
+
+static int multi_host_batch(Op op, const uint8_t* src_base, const uint64_t* src_off, const int32_t* src_len,
+                            uint8_t* dst_base, const uint64_t* dst_off, const int32_t* dst_cap,
+                            int32_t* result, size_t n, int param, const int* devices, int ndev)
+{
+    if (n == 0) return 0;
+    if (!src_base || !src_off || !src_len || !dst_base || !dst_off || !dst_cap || !result) return fail_arg("null pointer");
+    return run_sharded(n, devices, ndev, [&](size_t lo, size_t cnt) {
+        return host_batch(op, src_base, src_off + lo, src_len + lo, dst_base, dst_off + lo, dst_cap + lo, result + lo, cnt, param);
+    });
+}
+
 } // namespace b200
 
 using namespace b200;
@@ -684,6 +740,33 @@ int b200lz4_compress_fast_compact_host(const uint8_t* src_base, const uint64_t* 
     if (total) *total = running;
     guard.completed = true;
     return 0;
+}
+
+int b200lz4_compress_fast_batch_host_multi(const uint8_t* src_base, const uint64_t* src_off, const int32_t* src_len,
+                                           uint8_t* dst_base, const uint64_t* dst_off, const int32_t* dst_cap,
+                                           int32_t* result, size_t n, int max_src_len, const int* devices, int ndev)
+{ return multi_host_batch(OP_COMPRESS_FAST, src_base, src_off, src_len, dst_base, dst_off, dst_cap, result, n, max_src_len, devices, ndev); }
+int b200lz4_decompress_safe_batch_host_multi(const uint8_t* src_base, const uint64_t* src_off, const int32_t* src_len,
+                                             uint8_t* dst_base, const uint64_t* dst_off, const int32_t* dst_cap,
+                                             int32_t* result, size_t n, const int* devices, int ndev)
+{ return multi_host_batch(OP_DEC_SAFE, src_base, src_off, src_len, dst_base, dst_off, dst_cap, result, n, 0, devices, ndev); }
+int b200lz4_decompress_fast_batch_host_multi(const uint8_t* src_base, const uint64_t* src_off, const int32_t* src_avail,
+                                             uint8_t* dst_base, const uint64_t* dst_off, const int32_t* dst_len,
+                                             int32_t* result, size_t n, const int* devices, int ndev)
+{ return multi_host_batch(OP_DEC_FAST, src_base, src_off, src_avail, dst_base, dst_off, dst_len, result, n, 0, devices, ndev); }
+int b200xxh32_batch_host_multi(const uint8_t* base, const uint64_t* off, const int32_t* len, uint32_t seed,
+                               uint32_t* out, size_t n, const int* devices, int ndev)
+{
+    if (n == 0) return 0;
+    if (!base || !off || !len || !out) return fail_arg("null pointer");
+    return run_sharded(n, devices, ndev, [&](size_t lo, size_t cnt) { return hash_host_batch<uint32_t>(32, base, off + lo, len + lo, seed, out + lo, cnt); });
+}
+int b200xxh64_batch_host_multi(const uint8_t* base, const uint64_t* off, const int32_t* len, uint64_t seed,
+                               uint64_t* out, size_t n, const int* devices, int ndev)
+{
+    if (n == 0) return 0;
+    if (!base || !off || !len || !out) return fail_arg("null pointer");
+    return run_sharded(n, devices, ndev, [&](size_t lo, size_t cnt) { return hash_host_batch<uint64_t>(64, base, off + lo, len + lo, seed, out + lo, cnt); });
 }
 
 int b200lz4_context_count(void) { return g_contexts.load(std::memory_order_relaxed); }

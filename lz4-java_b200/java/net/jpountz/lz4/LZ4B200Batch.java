@@ -22,6 +22,40 @@ public final class LZ4B200Batch {
   static LongBuffer longs(int n) { return ByteBuffer.allocateDirect(8 * n).order(ByteOrder.nativeOrder()).asLongBuffer(); }
   static IntBuffer ints(int n) { return ByteBuffer.allocateDirect(4 * n).order(ByteOrder.nativeOrder()).asIntBuffer(); }
 
+  /** Number of usable B200 devices (b200lz4_device_count). */
+  public static int deviceCount() {
+    final int n = LZ4B200JNI.deviceCount();
+    if (n < 0) throw new LZ4Exception("B200 backend error " + n);
+    return n;
+  }
+
+  /** {@link #compressUniform(ByteBuffer, int, int, ByteBuffer)} range-sharded over the first {@code gpus} devices: GPU g
+   *  compresses blocks [g*n/gpus, (g+1)*n/gpus) on its own streams; same bytes as the single-GPU call. */
+  public static int[] compressUniform(ByteBuffer src, int blockSize, int n, ByteBuffer dst, int gpus) {
+    final int bound = LZ4Utils.maxCompressedLength(blockSize);
+    final LongBuffer so = longs(n), dof = longs(n);
+    final IntBuffer sl = ints(n), dc = ints(n), res = ints(n);
+    for (int i = 0; i < n; i++) { so.put(i, (long) i * blockSize); sl.put(i, blockSize); dof.put(i, (long) i * bound); dc.put(i, bound); }
+    final int rc = LZ4B200JNI.compressBatchMulti(src, so, sl, dst, dof, dc, res, n, blockSize, null, gpus);
+    if (rc != 0) throw new LZ4Exception("B200 backend error " + rc);
+    final int[] out = new int[n];
+    res.get(out);
+    for (int r : out) if (r <= 0) throw new LZ4Exception("maxDestLen is too small");
+    return out;
+  }
+
+  /** Inverse of the sharded {@link #compressUniform(ByteBuffer, int, int, ByteBuffer, int)}. */
+  public static void decompressUniform(ByteBuffer src, int[] compressedLen, int blockSize, ByteBuffer dst, int gpus) {
+    final int n = compressedLen.length;
+    final int bound = LZ4Utils.maxCompressedLength(blockSize);
+    final LongBuffer so = longs(n), dof = longs(n);
+    final IntBuffer sa = ints(n), dl = ints(n), res = ints(n);
+    for (int i = 0; i < n; i++) { so.put(i, (long) i * bound); sa.put(i, bound); dof.put(i, (long) i * blockSize); dl.put(i, blockSize); }
+    final int rc = LZ4B200JNI.decompressFastBatchMulti(src, so, sa, dst, dof, dl, res, n, null, gpus);
+    if (rc != 0) throw new LZ4Exception("B200 backend error " + rc);
+    for (int i = 0; i < n; i++) if (res.get(i) != compressedLen[i]) throw new LZ4Exception("Error decoding block " + i);
+  }
+
   /** Compresses n equally sized blocks laid out back to back in src into bound-sized slots of dst; returns per-block sizes. */
   public static int[] compressUniform(ByteBuffer src, int blockSize, int n, ByteBuffer dst) {
     final int bound = LZ4Utils.maxCompressedLength(blockSize);

@@ -30,5 +30,10 @@ enum LZ4B200JNI {
   static native int compressBatch(ByteBuffer src, LongBuffer srcOff, IntBuffer srcLen, ByteBuffer dst, LongBuffer dstOff, IntBuffer dstCap, IntBuffer result, int n, int maxSrcLen);
   static native int decompressFastBatch(ByteBuffer src, LongBuffer srcOff, IntBuffer srcAvail, ByteBuffer dst, LongBuffer dstOff, IntBuffer dstLen, IntBuffer result, int n);
   static native int decompressSafeBatch(ByteBuffer src, LongBuffer srcOff, IntBuffer srcLen, ByteBuffer dst, LongBuffer dstOff, IntBuffer dstCap, IntBuffer result, int n);
+  /* the same, range-sharded over several GPUs from this one JVM; devices: direct IntBuffer of device indices, or null for 0..ndev-1 */
+  static native int compressBatchMulti(ByteBuffer src, LongBuffer srcOff, IntBuffer srcLen, ByteBuffer dst, LongBuffer dstOff, IntBuffer dstCap, IntBuffer result, int n, int maxSrcLen, IntBuffer devices, int ndev);
+  static native int decompressFastBatchMulti(ByteBuffer src, LongBuffer srcOff, IntBuffer srcAvail, ByteBuffer dst, LongBuffer dstOff, IntBuffer dstLen, IntBuffer result, int n, IntBuffer devices, int ndev);
+  static native int decompressSafeBatchMulti(ByteBuffer src, LongBuffer srcOff, IntBuffer srcLen, ByteBuffer dst, LongBuffer dstOff, IntBuffer dstCap, IntBuffer result, int n, IntBuffer devices, int ndev);
+  static native int deviceCount();
   static native int registerDirectBuffer(ByteBuffer buf);
 }

@@ -124,6 +124,42 @@ JNIEXPORT jint JNICALL Java_net_jpountz_lz4_LZ4B200JNI_decompressSafeBatch
         (const uint64_t*)(*env)->GetDirectBufferAddress(env, dstOff), (const int32_t*)(*env)->GetDirectBufferAddress(env, dstCap),
         (int32_t*)(*env)->GetDirectBufferAddress(env, result), (size_t)n);
 }
+/* the same three calls range-sharded over several GPUs from this one JVM (b200lz4_*_batch_host_multi): `devices` is a
+ * direct IntBuffer of device indices, or null for devices 0..ndev-1 */
+static const int* device_list(JNIEnv* env, jobject devices)
+{ return devices != NULL ? (const int*)(*env)->GetDirectBufferAddress(env, devices) : NULL; }
+JNIEXPORT jint JNICALL Java_net_jpountz_lz4_LZ4B200JNI_compressBatchMulti
+  (JNIEnv* env, jclass cls, jobject src, jobject srcOff, jobject srcLen, jobject dst, jobject dstOff, jobject dstCap,
+   jobject result, jint n, jint maxSrcLen, jobject devices, jint ndev)
+{
+    return b200lz4_compress_fast_batch_host_multi(
+        (const uint8_t*)(*env)->GetDirectBufferAddress(env, src), (const uint64_t*)(*env)->GetDirectBufferAddress(env, srcOff),
+        (const int32_t*)(*env)->GetDirectBufferAddress(env, srcLen), (uint8_t*)(*env)->GetDirectBufferAddress(env, dst),
+        (const uint64_t*)(*env)->GetDirectBufferAddress(env, dstOff), (const int32_t*)(*env)->GetDirectBufferAddress(env, dstCap),
+        (int32_t*)(*env)->GetDirectBufferAddress(env, result), (size_t)n, maxSrcLen, device_list(env, devices), ndev);
+}
+JNIEXPORT jint JNICALL Java_net_jpountz_lz4_LZ4B200JNI_decompressFastBatchMulti
+  (JNIEnv* env, jclass cls, jobject src, jobject srcOff, jobject srcAvail, jobject dst, jobject dstOff, jobject dstLen,
+   jobject result, jint n, jobject devices, jint ndev)
+{
+    return b200lz4_decompress_fast_batch_host_multi(
+        (const uint8_t*)(*env)->GetDirectBufferAddress(env, src), (const uint64_t*)(*env)->GetDirectBufferAddress(env, srcOff),
+        (const int32_t*)(*env)->GetDirectBufferAddress(env, srcAvail), (uint8_t*)(*env)->GetDirectBufferAddress(env, dst),
+        (const uint64_t*)(*env)->GetDirectBufferAddress(env, dstOff), (const int32_t*)(*env)->GetDirectBufferAddress(env, dstLen),
+        (int32_t*)(*env)->GetDirectBufferAddress(env, result), (size_t)n, device_list(env, devices), ndev);
+}
+JNIEXPORT jint JNICALL Java_net_jpountz_lz4_LZ4B200JNI_decompressSafeBatchMulti
+  (JNIEnv* env, jclass cls, jobject src, jobject srcOff, jobject srcLen, jobject dst, jobject dstOff, jobject dstCap,
+   jobject result, jint n, jobject devices, jint ndev)
+{
+    return b200lz4_decompress_safe_batch_host_multi(
+        (const uint8_t*)(*env)->GetDirectBufferAddress(env, src), (const uint64_t*)(*env)->GetDirectBufferAddress(env, srcOff),
+        (const int32_t*)(*env)->GetDirectBufferAddress(env, srcLen), (uint8_t*)(*env)->GetDirectBufferAddress(env, dst),
+        (const uint64_t*)(*env)->GetDirectBufferAddress(env, dstOff), (const int32_t*)(*env)->GetDirectBufferAddress(env, dstCap),
+        (int32_t*)(*env)->GetDirectBufferAddress(env, result), (size_t)n, device_list(env, devices), ndev);
+}
+JNIEXPORT jint JNICALL Java_net_jpountz_lz4_LZ4B200JNI_deviceCount(JNIEnv* env, jclass cls)
+{ (void)env; (void)cls; return b200lz4_device_count(); }
 JNIEXPORT jint JNICALL Java_net_jpountz_lz4_LZ4B200JNI_registerDirectBuffer(JNIEnv* env, jclass cls, jobject buf)
 {
     return b200lz4_host_register((*env)->GetDirectBufferAddress(env, buf), (size_t)(*env)->GetDirectBufferCapacity(env, buf));

@@ -56,9 +56,13 @@ static inline cudaError_t cudaHostRegister(void*, size_t, unsigned) { return cud
 static inline cudaError_t cudaHostUnregister(void*) { return cudaSuccess; }
 static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t = nullptr) { if (n) std::memmove(d, s, n); return cudaSuccess; }
 static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t = nullptr) { std::memset(d, v, n); return cudaSuccess; }
-static inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
-static inline cudaError_t cudaSetDevice(int d) { return d == 0 ? cudaSuccess : 101; }
-static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
+namespace simt_rt {
+inline int device_count() { const char* e = std::getenv("SIMT_DEVICES"); int n = e ? std::atoi(e) : 1; return n < 1 ? 1 : n; }   // pretend GPUs (multi-device host logic)
+inline int& current_device() { static thread_local int d = 0; return d; }
+}
+static inline cudaError_t cudaGetDeviceCount(int* n) { *n = simt_rt::device_count(); return cudaSuccess; }
+static inline cudaError_t cudaSetDevice(int d) { if (d < 0 || d >= simt_rt::device_count()) return 101; simt_rt::current_device() = d; return cudaSuccess; }
+static inline cudaError_t cudaGetDevice(int* d) { *d = simt_rt::current_device(); return cudaSuccess; }
 static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = std::malloc(8); return cudaSuccess; }
 static inline cudaError_t cudaStreamDestroy(cudaStream_t s) { std::free(s); return cudaSuccess; }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }

@@ -798,3 +798,47 @@ def test_golden_calgary_on_gpu(b200, port, decoder):
         h = f.highCompressor(9).compress(d)
         assert port.decompress_safe(h, len(d)) == (len(d), d), b["name"]
         assert len(h) < len(base64.b64decode(b["fast_b64"])), (b["name"], len(h))
+
+
+def test_multi_gpu_range_sharded_host_batches(b200, checker):
+    """One process driving several GPUs (the single-JVM case): the *_multi calls cut the block list into
+    contiguous ranges, one worker thread + context per listed device, no exchange.  Output must be byte-identical to the
+    single-GPU call whatever the device list is.  A one-GPU box lists device 0 several times (the shards then share the
+    GPU but not their streams or staging); the emulator build pretends SIMT_DEVICES GPUs."""
+    lib = b200._native.lib()
+    ndev = lib.b200lz4_device_count()
+    assert ndev >= 1
+    lists = [1, [0, 0, 0], [0] * 7] + ([ndev, list(range(ndev))[::-1]] if ndev > 1 else [])
+    datas = [checker.datagen(rng_n, 0.5, 0.0, s).tobytes() for s, rng_n in enumerate([65536, 1, 0, 40000, 65536, 13, 70000, 5000, 65536, 300, 12, 65536, 100000])]
+    src, soff, slen = corpus.pack(datas)
+    coff, ccap, ctotal = _slots([b200.max_compressed_length(len(d)) for d in datas])
+    want_c = np.zeros(ctotal, dtype=np.uint8)
+    want_len = b200.batch.compress_fast_batch_host(src, soff, slen, want_c, coff, ccap)
+    want_h32 = b200.batch.xxh32_batch_host(src, soff, slen, 7)
+    want_h64 = b200.batch.xxh64_batch_host(src, soff, slen, 7)
+    doff, dcap, dtotal = _slots([len(d) for d in datas])
+    for devs in lists:
+        comp = np.zeros(ctotal, dtype=np.uint8)
+        clen = b200.batch.compress_fast_batch_host_multi(src, soff, slen, comp, coff, ccap, devs)
+        assert (clen == want_len).all(), devs
+        for k in range(len(datas)):
+            o = int(coff[k])
+            assert comp[o:o + int(clen[k])].tobytes() == want_c[o:o + int(clen[k])].tobytes(), (devs, k)
+        out = np.zeros(dtotal, dtype=np.uint8)
+        r = b200.batch.decompress_safe_batch_host_multi(comp, coff, clen, out, doff, dcap, devs)
+        out2 = np.zeros(dtotal, dtype=np.uint8)
+        r2 = b200.batch.decompress_fast_batch_host_multi(comp, coff, ccap, out2, doff, dcap, devs)
+        for k, d in enumerate(datas):
+            assert int(r[k]) == len(d) and int(r2[k]) == int(clen[k]), (devs, k)
+            o = int(doff[k])
+            assert out[o:o + len(d)].tobytes() == d and out2[o:o + len(d)].tobytes() == d, (devs, k)
+        assert (b200.batch.xxh32_batch_host_multi(src, soff, slen, devs, 7) == want_h32).all()
+        assert (b200.batch.xxh64_batch_host_multi(src, soff, slen, devs, 7) == want_h64).all()
+    # fewer blocks than devices, no blocks, and a device that does not exist
+    two = b200.batch.compress_fast_batch_host_multi(src, soff[:2], slen[:2], np.zeros(ctotal, dtype=np.uint8), coff[:2], ccap[:2], [0] * 5)
+    assert (two == want_len[:2]).all()
+    assert len(b200.batch.xxh64_batch_host_multi(src, soff[:0], slen[:0], 3)) == 0
+    with pytest.raises(b200.B200Error, match="device"):
+        b200.batch.xxh32_batch_host_multi(src, soff, slen, [0, ndev + 5])
+    # the calling thread keeps working on its own device afterwards
+    assert (b200.batch.xxh32_batch_host(src, soff, slen, 7) == want_h32).all()
