@@ -158,6 +158,32 @@ class Port(_Lib):
         r = self.L.orc_frame_decompress(_ptr(s), len(s), _ptr(d), cap)
         return r, d[: max(r, 0)].tobytes()
 
+    # ---- lz4-java's pure-Java backend restated (lz4_java_port_oracle.c; PARITY UNPINNED: no JVM here)
+    def java_compress(self, src, cap: int | None = None):
+        """LZ4JavaSafeCompressor.compress -> bytes, or None where Java throws LZ4Exception"""
+        s = _as_u8(src)
+        cap = self.compress_bound(len(s)) if cap is None else cap
+        d = np.empty(max(cap, 1), dtype=np.uint8)
+        self.L.orc_java_compress.restype = C.c_int
+        r = self.L.orc_java_compress(_ptr(s), len(s), _ptr(d), cap)
+        return None if r < 0 else d[:r].tobytes()
+
+    def java_decompress_safe(self, src, cap: int):
+        """LZ4JavaSafeSafeDecompressor -> (bytes written or -1, output)"""
+        s = _as_u8(src)
+        d = np.zeros(max(cap, 1) + 8, dtype=np.uint8)
+        self.L.orc_java_decompress_safe.restype = C.c_int
+        r = self.L.orc_java_decompress_safe(_ptr(s), len(s), _ptr(d), cap)
+        return r, d[: max(r, 0)].tobytes()
+
+    def java_decompress_fast(self, src, n: int):
+        """LZ4JavaSafeFastDecompressor -> (bytes read or -1, output); len(src) is the readable array length"""
+        s = _as_u8(src)
+        d = np.zeros(max(n, 1) + 8, dtype=np.uint8)
+        self.L.orc_java_decompress_fast.restype = C.c_int
+        r = self.L.orc_java_decompress_fast(_ptr(s), len(s), _ptr(d), n)
+        return r, d[:n].tobytes() if r >= 0 else b""
+
     # ---- lz4-java's own containers
     def lz4block_compress(self, src, block_size=65536) -> bytes:
         s = _as_u8(src)

@@ -14,6 +14,11 @@ MALFORMED = [
     bytes([96, 42, 43, 44, 45, 46, 47, 5, 0, 1, 2]),
     bytes([96, 42, 43, 44, 45, 46, 47, 5, 0, 1, 2, 3]),
     bytes([96, 42, 43, 44, 45, 46, 47, 5, 0, 1, 2, 3, 4]),
+    # exactly the arrays LZ4Test.java:390-397 builds: the 9 bytes above + a token of i literals + i zero bytes, i = 1..4
+    bytes([96, 42, 43, 44, 45, 46, 47, 5, 0, 1 << 4, 0]),
+    bytes([96, 42, 43, 44, 45, 46, 47, 5, 0, 2 << 4, 0, 0]),
+    bytes([96, 42, 43, 44, 45, 46, 47, 5, 0, 3 << 4, 0, 0, 0]),
+    bytes([96, 42, 43, 44, 45, 46, 47, 5, 0, 4 << 4, 0, 0, 0, 0]),
 ]
 
 

@@ -842,3 +842,35 @@ def test_multi_gpu_range_sharded_host_batches(b200, checker):
         b200.batch.xxh32_batch_host_multi(src, soff, slen, [0, ndev + 5])
     # the calling thread keeps working on its own device afterwards
     assert (b200.batch.xxh32_batch_host(src, soff, slen, 7) == want_h32).all()
+
+
+def test_cross_backend_with_the_java_port(b200, port, decoder):
+    """LZ4Test.java:305-324 ties every compressor to every decompressor of every backend.  The pure-Java backend
+    (LZ4Factory.safeInstance(), BASELINE configs[0]) is available here only as a restatement (oracle/lz4_java_port_oracle.c,
+    unpinned): its streams must decode bit-exactly on the GPU with the right return values, and the GPU compressors'
+    streams must be accepted by the Java decoders' rule set (decompress.template), which differs from lz4.c's."""
+    items = [(n, bytes(d)) for n, d in corpus.blocks(port)]
+    jcomp = [port.java_compress(d) for _, d in items]
+    assert all(c is not None for c in jcomp)
+    src, soff, slen = corpus.pack([c + bytes(64) for c in jcomp])
+    exact = np.array([len(c) for c in jcomp], dtype=np.int32)
+    doff, dcap, total = _slots([len(d) for _, d in items])
+    out, out2 = np.zeros(total, dtype=np.uint8), np.zeros(total, dtype=np.uint8)
+    r = b200.batch.decompress_safe_batch_host(src, soff, exact, out, doff, dcap)
+    r2 = b200.batch.decompress_fast_batch_host(src, soff, slen, out2, doff, dcap)
+    for k, (name, d) in enumerate(items):
+        assert int(r[k]) == len(d) and int(r2[k]) == len(jcomp[k]), name
+        o = int(doff[k])
+        assert out[o:o + len(d)].tobytes() == d and out2[o:o + len(d)].tobytes() == d, name
+    if decoder != "batched":
+        return
+    # the GPU compressors' streams under the Java decoders
+    psrc, poff, plen = corpus.pack([d for _, d in items])
+    coff, ccap, ctotal = _slots([b200.max_compressed_length(len(d)) for _, d in items])
+    for fn in (b200.batch.compress_fast_batch_host, b200.batch.compress_hc_batch_host):
+        comp = np.zeros(ctotal, dtype=np.uint8)
+        clen = fn(psrc, poff, plen, comp, coff, ccap)
+        for k, (name, d) in enumerate(items):
+            c = comp[int(coff[k]):int(coff[k]) + int(clen[k])].tobytes()
+            assert port.java_decompress_safe(c, len(d)) == (len(d), d), (fn.__name__, name)
+            assert port.java_decompress_fast(c + bytes(16), len(d)) == (len(c), d), (fn.__name__, name)

@@ -161,3 +161,40 @@ def test_golden_calgary_streams(port):
         rf, df = port.decompress_fast(hc, b["len"])
         assert rf == len(hc) and df == d, b["name"]
         assert port.compress(d) == fast, b["name"]
+
+
+def test_java_port_restatement_cross_checks(port):
+    """the pure-Java backend restated (oracle/lz4_java_port_oracle.c; unpinned — no JVM here) is
+    tied to the pinned C restatement the way LZ4Test.java:305-324 ties the backends to each other: every compressor's
+    stream under every decompressor.  Also the vectors LZ4Test.java:350-419 expects EVERY backend to reject."""
+    import base64
+    items = corpus.blocks(port)
+    cal = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "calgary_lz4.json")))["blocks"]
+    items += [(b["name"], port.decompress_safe(base64.b64decode(b["fast_b64"]), b["len"])[1]) for b in cal]
+    sizes_c = sizes_j = 0
+    for name, d in items:
+        d = bytes(d)
+        cj = port.java_compress(d)
+        assert cj is not None and len(cj) <= port.compress_bound(len(d)), name
+        cc = port.compress(d)
+        sizes_c += len(cc); sizes_j += len(cj)
+        for c in (cj, cc):
+            assert port.decompress_safe(c, len(d)) == (len(d), d), name                        # C decoders read both
+            assert port.decompress_fast(c + bytes(16), len(d)) == (len(c), d), name
+            assert port.java_decompress_safe(c, len(d)) == (len(d), d), name                   # Java decoders read both
+            assert port.java_decompress_safe(c, len(d) + 50) == (len(d), d), name
+            assert port.java_decompress_fast(c + bytes(16), len(d)) == (len(c), d), name
+        if len(d) > 20:
+            assert port.java_decompress_safe(cj, len(d) - 1)[0] < 0, name                      # LZ4Test.java:240-252
+            assert port.java_decompress_fast(cj + bytes(16), len(d) - 1)[0] < 0 or len(d) < 14, name
+        assert port.java_compress(d, max(0, len(cj) - 1)) is None or len(d) == 0, name        # maxDestLen is too small
+    assert 0.9 < sizes_j / sizes_c < 1.1            # same family of parse: sizes within a few percent of each other
+    # LZ4Test.java:350-361: offset 0 must neither throw nor hang, in any backend
+    v0 = corpus.MALFORMED[0]
+    assert port.java_decompress_safe(v0, 20)[0] == 13 and port.decompress_safe(v0, 20)[0] == 13
+    assert port.java_decompress_fast(v0, 13)[0] == 13 and port.decompress_fast(v0 + bytes(8), 13)[0] == 13
+    # LZ4Test.java:363-419: ending with a match / with fewer than 5 literals must throw, in every backend
+    for v in corpus.MALFORMED[1:]:
+        assert port.java_decompress_safe(v, 20)[0] < 0 and port.decompress_safe(v, 20)[0] < 0, v.hex()
+        for n in (10, 20):
+            assert port.java_decompress_fast(v, n)[0] < 0 and port.decompress_fast(v + bytes(32), n)[0] < 0, (v.hex(), n)
