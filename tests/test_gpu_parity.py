@@ -874,3 +874,59 @@ def test_cross_backend_with_the_java_port(b200, port, decoder):
             c = comp[int(coff[k]):int(coff[k]) + int(clen[k])].tobytes()
             assert port.java_decompress_safe(c, len(d)) == (len(d), d), (fn.__name__, name)
             assert port.java_decompress_fast(c + bytes(16), len(d)) == (len(c), d), (fn.__name__, name)
+
+
+def test_uncompress_worst_case_literal_only_blocks(b200, checker, decoder):
+    """LZ4Test.java:89-154 (testUncompressWorstCase / testUncompressSafeWorstCase): hand-built literals-only blocks — one
+    token, the 255-chain, the bytes — up to 100 KiB (longer than anything the compressors emit for 64 KiB blocks),
+    including the seed the reference pins for lengths < 16"""
+    rng = random.Random(0x69CCC652)
+    lens = list(range(0, 18)) + [254, 255, 256, 269, 270, 271, 4096, 65535, 65536, 65537, 100 * 1024] + [rng.randrange(100 * 1024) for _ in range(6)]
+    plain, comp = [], []
+    for n in lens:
+        d = bytes(rng.randrange(rng.choice([1, 2, 255, 256]) + 1) & 0xFF for _ in range(n))
+        c = bytearray()
+        if n >= 15:
+            c.append(15 << 4); rest = n - 15
+            while rest >= 255:
+                c.append(255); rest -= 255
+            c.append(rest)
+        else:
+            c.append(n << 4)
+        plain.append(d); comp.append(bytes(c) + d)
+    src, soff, slen = corpus.pack([c + bytes(32) for c in comp])
+    exact = np.array([len(c) for c in comp], dtype=np.int32)
+    doff, dcap, total = _slots(lens)
+    out, out2 = np.zeros(total, dtype=np.uint8), np.zeros(total, dtype=np.uint8)
+    r = b200.batch.decompress_safe_batch_host(src, soff, exact, out, doff, dcap)
+    r2 = b200.batch.decompress_fast_batch_host(src, soff, slen, out2, doff, dcap)
+    for k, d in enumerate(plain):
+        assert (int(r[k]), int(r2[k])) == (len(d), len(comp[k])), (k, len(d))
+        assert checker.decompress_safe(comp[k], len(d)) == (len(d), d)
+        o = int(doff[k])
+        assert out[o:o + len(d)].tobytes() == d and out2[o:o + len(d)].tobytes() == d, (k, len(d))
+
+
+@pytest.mark.skipif("sim" in os.environ.get("B200LZ4_TEST_SO", ""), reason="8 GiB of hashing: not for the CPU emulator build")
+def test_streaming_hash_past_4gb(b200, port):
+    """XXHash64Test.java:149-170 / XXHash32Test.java (test4GB): a streaming state fed more than 2^32 bytes — XXH32 keeps
+    its length modulo 2^32 (xxhash.c:437-563: total_len_32 + large_len), XXH64 a 64-bit one — checked against the CPU
+    restatement fed the same chunks, with getValue() read (and required idempotent) along the way"""
+    chunk = port.datagen((1 << 26) + 1000, 0.5, 0.0, 41)
+    off, ln = 3, (1 << 26) + 1000 - 3 - 517
+    view = chunk[off:off + ln]
+    seed = 0x1234567
+    h32, h64 = b200.StreamingXXHash32(seed), b200.StreamingXXHash64(seed * 0x100000001)
+    import ctypes as C
+    L = port.L
+    s32 = C.create_string_buffer(L.orc_xxh32_state_size()); s64 = C.create_string_buffer(L.orc_xxh64_state_size())
+    L.orc_xxh32_reset(s32, seed); L.orc_xxh64_reset(s64, seed * 0x100000001)
+    total = 0
+    while total < (1 << 32) + (1 << 27):
+        h32.update(chunk, off, ln); h64.update(chunk, off, ln)
+        L.orc_xxh32_update(s32, view.ctypes.data, ln); L.orc_xxh64_update(s64, view.ctypes.data, ln)
+        total += ln
+        if total > (1 << 32) - (1 << 27) or total < (1 << 28):
+            assert h32.getValue() == L.orc_xxh32_digest(s32) == h32.getValue(), total
+            assert h64.getValue() == L.orc_xxh64_digest(s64) == h64.getValue(), total
+    h32.close(); h64.close()
