@@ -421,6 +421,13 @@ static cudaError_t launch_v2(const BatchArgs& a, cudaStream_t st)
 #ifndef B200_V3_MINB12
 #define B200_V3_MINB12 16
 #endif
+// B200_V3_RUNS = 1 (experimental, unmeasured; DESIGN.md "Round-2 plan"): warp L also publishes which hits START a run
+// (a hit continues a run when the position before it hit with the same distance), and warp P ranks and measures run
+// starts only.  A sequence that has to start inside a run (at the end of the previous one) takes the run's distance and
+// ends where the run start's match ends, so nothing is measured twice.  Same greedy parse, same output bytes as 0.
+#ifndef B200_V3_RUNS
+#define B200_V3_RUNS 0
+#endif
 #ifdef B200_HOST_SIM
 __device__ __forceinline__ void bar_arrive(int id) { simt::bar_arrive(id, 64); }
 __device__ __forceinline__ void bar_wait(int id) { simt::bar_sync(id, 64); }
@@ -464,6 +471,9 @@ lz4_compress_fast3_kernel(const uint8_t* __restrict__ src_base, const uint64_t* 
     uint32_t* s_mask = reinterpret_cast<uint32_t*>(smem_raw + TABLE_BYTES + NB * 256 + NB * 256);   // [NB][4] hit masks
     int* s_cnt = reinterpret_cast<int*>(s_mask + 4 * NB);                                   // [NB] records per buffer
     uint8_t* s_hit = reinterpret_cast<uint8_t*>(s_cnt + 4);                                 // [128] ranked hit positions (warp P's scratch)
+#if B200_V3_RUNS
+    uint32_t* s_rmask = reinterpret_cast<uint32_t*>(s_hit + 128);                           // [NB][4] run-start masks
+#endif
 
     const uint32_t b = blockIdx.x;
     if (b >= nblocks) return;
@@ -524,6 +534,20 @@ lz4_compress_fast3_kernel(const uint8_t* __restrict__ src_base, const uint64_t* 
         uint32_t gw = nib << (4 * (lane & 7));        // OR over each group of 8 lanes (butterfly: all lanes in step)
         gw |= __shfl_xor_sync(B200_FULL, gw, 1); gw |= __shfl_xor_sync(B200_FULL, gw, 2); gw |= __shfl_xor_sync(B200_FULL, gw, 4);
         if ((lane & 7) == 0) s_mask[4 * buf + (lane >> 3)] = gw;
+#if B200_V3_RUNS
+        // dd[j] is 0 for a miss and >= 1 for a hit: position p continues a run when dd[p] == dd[p-1] != 0.  Position 0 of
+        // a chunk always starts a run (the previous chunk's hits are another buffer's business).
+        uint32_t pd = __shfl_up_sync(B200_FULL, dd[3], 1);
+        if (lane == 0) pd = 0;
+        uint32_t rs = nib;
+        if (dd[0] && dd[0] == pd) rs &= ~1u;
+        if (dd[1] && dd[1] == dd[0]) rs &= ~2u;
+        if (dd[2] && dd[2] == dd[1]) rs &= ~4u;
+        if (dd[3] && dd[3] == dd[2]) rs &= ~8u;
+        uint32_t gr = rs << (4 * (lane & 7));
+        gr |= __shfl_xor_sync(B200_FULL, gr, 1); gr |= __shfl_xor_sync(B200_FULL, gr, 2); gr |= __shfl_xor_sync(B200_FULL, gr, 4);
+        if ((lane & 7) == 0) s_rmask[4 * buf + (lane >> 3)] = gr;
+#endif
     };
 
     // ------------------------------------------------------------------ lay out the sequences of one chunk (warp E, or L)
@@ -602,6 +626,139 @@ lz4_compress_fast3_kernel(const uint8_t* __restrict__ src_base, const uint64_t* 
 
     // ------------------------------------------------------------------ the greedy walk of one chunk (warp P)
     int ip = 0, anchor = 0;
+#if B200_V3_RUNS
+    auto walk = [&](int c) {
+        const int cp0 = 128 * c - int(ph), buf = c % NB;
+        const bool inner = cp0 >= 4 && cp0 + 128 + 32 <= n;  // every measurement window of this chunk lies inside the block
+        int k = 0;
+        // true when chunk position e is a hit that continues a run (warp-uniform or per-lane e)
+        auto continues = [&](int e) -> bool {
+            if (e <= 0 || e >= 128) return false;
+            return (((s_mask[4 * buf + (e >> 5)] & ~s_rmask[4 * buf + (e >> 5)]) >> (e & 31)) & 1u) != 0;
+        };
+        while (ip < cp0 + 128) {
+            // ---- rank the run starts from ip on; if ip itself lies inside a run, from that run's start
+            const int r0 = max(ip - cp0, 0);
+            const bool mid0 = continues(r0);
+            int start0 = r0;
+            if (mid0) {
+                #pragma unroll
+                for (int kk = 3; kk >= 0; kk--) {
+                    uint32_t m = s_rmask[4 * buf + kk];
+                    const int hi = r0 - 32 * kk;             // keep positions below r0
+                    if (hi <= 0) m = 0; else if (hi < 32) m &= (1u << hi) - 1u;
+                    if (m && start0 == r0) start0 = 32 * kk + 31 - __clz(m);
+                }
+            }
+            int nh = 0;
+            #pragma unroll
+            for (int kk = 0; kk < 4; kk++) {
+                uint32_t m = s_rmask[4 * buf + kk];
+                const int lo = start0 - 32 * kk;
+                if (lo >= 32) m = 0; else if (lo > 0) m &= 0xFFFFFFFFu << lo;
+                const int rk = nh + __popc(m & ((1u << lane) - 1u));
+                if (((m >> lane) & 1u) && rk < 32) s_hit[rk] = uint8_t(32 * kk + lane);
+                nh += __popc(m);
+            }
+            __syncwarp();
+            if (nh == 0) break;
+            // ---- every lane measures one run start
+            int ms = 0, ml = 0, back = 0, dist = 1; bool longer = false;
+            const bool have = lane < nh;
+            if (have) {
+                ms = cp0 + s_hit[lane];
+                dist = s_dist[128 * buf + (ms - cp0)];
+                const int mc = ms - dist;
+                const int lim = matchlimit - ms, capl = min(lim, 32);
+                const uint32_t am = uint32_t(ms + 4) + ph, ac = uint32_t(mc + 4) + ph;     // +4: (pos - 4) never negative in the view
+                const uint32_t lastw = (uint32_t(n - 1) + ph) >> 2;
+                uint32_t wm[7], wc[7];
+                if (inner) {
+                    const uint32_t* pm = wsrc + (am >> 2) - 2;
+                    const uint32_t* pc = wsrc + (mc >= 4 ? (ac >> 2) - 2 : 0u);
+                    #pragma unroll
+                    for (int t = 0; t < 7; t++) { wm[t] = pm[t]; wc[t] = pc[t]; }
+                } else {
+                    #pragma unroll
+                    for (int t = 0; t < 7; t++) {
+                        wm[t] = wsrc[min((am >> 2) - 2 + t, lastw)];
+                        wc[t] = mc >= 4 ? wsrc[min((ac >> 2) - 2 + t, lastw)] : 0u;
+                    }
+                }
+                const uint32_t sm = (am & 3u) * 8u, sc = (ac & 3u) * 8u;
+                if (mc >= 4) {
+                    const uint32_t x = __funnelshift_r(wm[0], wm[1], sm) ^ __funnelshift_r(wc[0], wc[1], sc);
+                    back = x ? (__clz(x) >> 3) : 4;
+                }
+                ml = 4;
+                if (mc >= 4) {
+                    #pragma unroll
+                    for (int t = 2; t < 6; t++) {
+                        const uint32_t x = __funnelshift_r(wm[t], wm[t + 1], sm) ^ __funnelshift_r(wc[t], wc[t + 1], sc);
+                        if (x) { ml += (__ffs(x) - 1) >> 3; goto measured; }
+                        ml += 4;
+                    }
+                }
+                while (ml < capl) {
+                    const uint32_t x = ld4(ms + ml) ^ ld4(mc + ml);
+                    if (x) { ml += (__ffs(x) - 1) >> 3; break; }
+                    ml += 4;
+                }
+            measured:
+                if (ml >= capl) { ml = capl; longer = capl < lim; }
+            }
+            // keys ascend (ranked positions); empty lanes sort to the back.  succ(v) = first lane whose run starts at or after v.
+            const int key = have ? ms : 0x7FFFFFFF;
+            const int key31 = __shfl_sync(B200_FULL, key, 31);
+            auto succ = [&](int v) -> int {
+                int q = 0;
+                #pragma unroll
+                for (int st = 16; st; st >>= 1) { const int pk = __shfl_sync(B200_FULL, key, q + st - 1); if (pk < v) q += st; }
+                if (q == 31 && key31 < v) q = 32;
+                return q;
+            };
+            int end = ms + ml;
+            // where the chain goes after this lane's match: the run start at or after its end, or — when the end is a hit
+            // inside a run — that run (the nearest run start before the end), entered in the middle
+            const int nxt = succ(end) | (int(continues(end - cp0)) << 8);
+            const unsigned hm = __ballot_sync(B200_FULL, have);
+            const unsigned lm = __ballot_sync(B200_FULL, have && longer);
+            unsigned sel = 0, msel = 0;
+            int j = 0; bool jmid = mid0;
+            while (j < 32 && ((hm >> j) & 1u)) {            // the greedy chain: one shuffle per selected sequence
+                sel |= 1u << j;
+                if (jmid) msel |= 1u << j;
+                int step;
+                if ((lm >> j) & 1u) {                        // 32 bytes matched and more to go: finish with the whole warp
+                    const int jend = __shfl_sync(B200_FULL, end, j), jdist = __shfl_sync(B200_FULL, dist, j);
+                    const int ext = match_extend(InGlobal{src}, jend, jend - jdist, matchlimit - jend, lane);
+                    if (lane == j) { ml += ext; end += ext; }
+                    step = succ(jend + ext) | (int(continues(jend + ext - cp0)) << 8);
+                } else step = __shfl_sync(B200_FULL, nxt, j);
+                const int nj = step & 0xFF;
+                jmid = (step >> 8) != 0;
+                if (jmid && nj == 32 && nh > 32) { j = 32; break; }     // the run in question was not ranked into this round
+                j = jmid ? nj - 1 : nj;
+            }
+            {
+                const unsigned below = sel & ((1u << lane) - 1u);
+                int pend = __shfl_sync(B200_FULL, end, (31 - __clz(below)) & 31);     // end of the previous selected sequence
+                if (!below) pend = anchor;
+                if ((sel >> lane) & 1u) {
+                    int start, len;
+                    if ((msel >> lane) & 1u) { start = pend; len = end - pend; }         // entered inside the run: no catch-up
+                    else { const int bk = min(back, ms - pend); start = ms - bk; len = ml + bk; }
+                    s_rec[32 * buf + k + __popc(below)] = make_uint2(uint32_t(start) | (uint32_t(dist) << 16), uint32_t(len));
+                }
+                k += __popc(sel);
+                ip = anchor = __shfl_sync(B200_FULL, end, 31 - __clz(sel));
+            }
+            if (nh <= 32) break;                             // every run start of the chunk was in this round
+            __syncwarp();                                    // s_hit is re-ranked from the new ip
+        }
+        if (lane == 0) s_cnt[buf] = k;
+    };
+#else
     auto walk = [&](int c) {
         const int cp0 = 128 * c - int(ph), buf = c % NB;
         const bool inner = cp0 >= 4 && cp0 + 128 + 32 <= n;  // every measurement window of this chunk lies inside the block
@@ -708,6 +865,8 @@ lz4_compress_fast3_kernel(const uint8_t* __restrict__ src_base, const uint64_t* 
         if (lane == 0) s_cnt[buf] = k;
     };
 
+#endif
+
     if (role == 0) {
         for (int i = lane; i < TABLE_BYTES / 16; i += 32) reinterpret_cast<uint4*>(table)[i] = make_uint4(0, 0, 0, 0);
         __syncwarp();
@@ -747,7 +906,7 @@ lz4_compress_fast3_kernel(const uint8_t* __restrict__ src_base, const uint64_t* 
 template <int HASH_LOG, bool SPARSE>
 static cudaError_t launch_v3(const BatchArgs& a, cudaStream_t st)
 {
-    const size_t smem = (2u << HASH_LOG) + B200_V3_NB * (256 + 256 + 16) + 16 + 128;
+    const size_t smem = (2u << HASH_LOG) + B200_V3_NB * (256 + 256 + 16) + 16 + 128 + (B200_V3_RUNS ? B200_V3_NB * 16 : 0);
     auto k = lz4_compress_fast3_kernel<HASH_LOG, SPARSE>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

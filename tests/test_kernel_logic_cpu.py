@@ -380,3 +380,44 @@ def test_host_layer_on_the_emulator_library():
                         "-W", "ignore::DeprecationWarning", "-k", "factory_api or compact_host or xxhash_streaming or self_roundtrip or failed_pipeline or contexts_are_reused or jni_shim or multi_gpu_range"],
                        env=env, cwd=ROOT, capture_output=True, text=True)
     assert r.returncode == 0 and "8 passed" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+# ---------------------------------------------------------------------------------------------- experimental build knobs
+def test_run_start_parser_variant_emits_the_same_bytes(csim, port):
+    """B200_V3_RUNS=1 (DESIGN.md, round-2 plan; off by default, not yet measured): warp P ranks and measures run STARTS only
+    and enters a run in the middle when the previous sequence ends inside it.  It must be the same greedy parse: byte-identical
+    output to the default build for every table variant, full and limited capacity — on the corpus and on shapes made to
+    stress runs (short periods, alternating distances, > 32 run starts per 128-byte chunk)."""
+    out = os.path.join(HERE, "simt", "_build")
+    so = os.path.join(out, "libcompsim_runs.so")
+    subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-Wno-unknown-pragmas", "-Wno-attributes", "-DB200_HOST_SIM",
+                    "-DB200_V3_RUNS=1", "-I" + os.path.join(HERE, "simt"), "-I" + os.path.join(ROOT, "lz4-java_b200", "csrc"),
+                    os.path.join(HERE, "simt", "comp_harness.cpp"), "-o", so], check=True, capture_output=True)
+    runs = ctypes.CDLL(so)
+    runs.sim_compress_fast.restype = ctypes.c_int
+    runs.sim_compress_fast.argtypes = csim.sim_compress_fast.argtypes
+
+    def run(lib, b, cap, hl, sparse):
+        s = _src(b); d = np.full(cap + 2 * PAD, 0x55, dtype=np.uint8)
+        r = lib.sim_compress_fast(s.ctypes.data + PAD, len(b), d.ctypes.data + PAD, cap, 3, hl, 1, sparse, 0)
+        assert (d[:PAD] == 0x55).all() and (d[PAD + cap:] == 0x55).all()
+        return r, d[PAD:PAD + max(r, 0)].tobytes()
+
+    rng = random.Random(5)
+    items = [(n, bytes(d)) for n, d in corpus.blocks(port, big=False)]
+    words = [rng.randbytes(rng.choice([4, 5, 6, 7])) for _ in range(12)]
+    for n in (300, 5000, 30000):
+        items += [(f"period3_{n}", (b"abc" * n)[:n]), (f"period5_{n}", (b"abcde" * n)[:n]),
+                  (f"bits_{n}", bytes(rng.choice(b"ab") for _ in range(n))),
+                  (f"words_{n}", b"".join(rng.choice(words) + rng.randbytes(rng.choice([0, 1, 2])) for _ in range(n // 5))[:n])]
+    for mp, seed in ((0.2, 1), (0.5, 2), (0.8, 3), (0.95, 4)):
+        items.append((f"rdg{mp}", port.datagen(65536, mp, 0.0, seed).tobytes()))
+    for name, d in items:
+        for hl, sp in ((13, 0), (12, 0), (13, 1)):
+            cap = port.compress_bound(len(d))
+            want = run(csim, d, cap, hl, sp)
+            assert run(runs, d, cap, hl, sp) == want, (name, hl, sp)
+            if hl == 13 and sp == 0 and want[0] > 0:
+                assert port.decompress_safe(want[1], len(d)) == (len(d), d), name
+                for cap2 in (want[0] - 1, max(0, want[0] - rng.randrange(2, 40))):
+                    assert run(runs, d, cap2, hl, sp) == run(csim, d, cap2, hl, sp), (name, cap2)
