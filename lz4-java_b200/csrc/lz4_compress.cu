@@ -428,6 +428,16 @@ static cudaError_t launch_v2(const BatchArgs& a, cudaStream_t st)
 #ifndef B200_V3_RUNS
 #define B200_V3_RUNS 0
 #endif
+// B200_V3_SPLIT = 1 (experimental, unmeasured; needs B200_V3_RUNS and the two-warp build): the parser warp also lays out
+// the sequence headers (sizes, prefix sum of output offsets, token / length bytes / offset) while it still holds the
+// selected sequences in registers, and hands warp L only (literal source, literal count, destination) triples, so L is
+// left with lookup + literal copies.  Same output bytes.
+#ifndef B200_V3_SPLIT
+#define B200_V3_SPLIT 0
+#endif
+#if B200_V3_SPLIT && !(B200_V3_RUNS && B200_V3_WARPS == 2)
+#error "B200_V3_SPLIT needs B200_V3_RUNS=1 and B200_V3_WARPS=2"
+#endif
 #ifdef B200_HOST_SIM
 __device__ __forceinline__ void bar_arrive(int id) { simt::bar_arrive(id, 64); }
 __device__ __forceinline__ void bar_wait(int id) { simt::bar_sync(id, 64); }
@@ -467,12 +477,20 @@ lz4_compress_fast3_kernel(const uint8_t* __restrict__ src_base, const uint64_t* 
     B200_DYN_SMEM(smem_raw, 128);
     uint16_t* table = reinterpret_cast<uint16_t*>(smem_raw);
     uint16_t* s_dist = reinterpret_cast<uint16_t*>(smem_raw + TABLE_BYTES);                 // [NB][128] distance per position, 0 = no match
+    constexpr int REC_BYTES = B200_V3_SPLIT ? 512 : 256;
+#if B200_V3_SPLIT
+    uint4* s_rec4 = reinterpret_cast<uint4*>(smem_raw + TABLE_BYTES + NB * 256);            // [NB][32]  x = literal source, y = literal count, z = destination
+#else
     uint2* s_rec = reinterpret_cast<uint2*>(smem_raw + TABLE_BYTES + NB * 256);             // [NB][32]  x = start | distance << 16, y = length
-    uint32_t* s_mask = reinterpret_cast<uint32_t*>(smem_raw + TABLE_BYTES + NB * 256 + NB * 256);   // [NB][4] hit masks
+#endif
+    uint32_t* s_mask = reinterpret_cast<uint32_t*>(smem_raw + TABLE_BYTES + NB * 256 + NB * REC_BYTES);   // [NB][4] hit masks
     int* s_cnt = reinterpret_cast<int*>(s_mask + 4 * NB);                                   // [NB] records per buffer
     uint8_t* s_hit = reinterpret_cast<uint8_t*>(s_cnt + 4);                                 // [128] ranked hit positions (warp P's scratch)
 #if B200_V3_RUNS
     uint32_t* s_rmask = reinterpret_cast<uint32_t*>(s_hit + 128);                           // [NB][4] run-start masks
+#endif
+#if B200_V3_SPLIT
+    int* s_state = reinterpret_cast<int*>(s_rmask + 4 * NB);                                // [NB][4] output offset, end of the last sequence, failed
 #endif
 
     const uint32_t b = blockIdx.x;
@@ -552,6 +570,36 @@ lz4_compress_fast3_kernel(const uint8_t* __restrict__ src_base, const uint64_t* 
 
     // ------------------------------------------------------------------ lay out the sequences of one chunk (warp E, or L)
     int op = 0, prev_end = 0; bool fail = false;
+#if B200_V3_SPLIT
+    auto emit = [&](int c) {                               // warp L: only the literal bytes are left to copy
+        const int buf = c % NB;
+        const int cnt = s_cnt[buf];
+        op = s_state[4 * buf]; prev_end = s_state[4 * buf + 1]; fail = s_state[4 * buf + 2] != 0;
+        if (fail || cnt == 0) return;
+        uint4 r = make_uint4(0, 0, 0, 0);
+        if (lane < cnt) r = s_rec4[32 * buf + lane];
+        const int pe = int(r.x), lit = int(r.y), lpos = int(r.z);
+        uint8_t* lo = dst + lpos;
+        const int sn = min(lit, 16);
+        const int mx = __reduce_max_sync(B200_FULL, sn);
+        for (int t = 0; t < mx; t += 4) {
+            if (t < sn) {
+                const uint32_t v = ld4(pe + t);
+                lo[t] = uint8_t(v);
+                if (t + 1 < sn) lo[t + 1] = uint8_t(v >> 8);
+                if (t + 2 < sn) lo[t + 2] = uint8_t(v >> 16);
+                if (t + 3 < sn) lo[t + 3] = uint8_t(v >> 24);
+            }
+        }
+        for (unsigned lm = __ballot_sync(B200_FULL, lit > 16); lm; lm &= lm - 1) {
+            const int k = __ffs(lm) - 1;
+            const int ka = __shfl_sync(B200_FULL, pe, k);
+            const int kl = __shfl_sync(B200_FULL, lit, k);
+            const int ko = __shfl_sync(B200_FULL, lpos, k);
+            warp_copy(dst + ko + 16, src + ka + 16, kl - 16, lane);
+        }
+    };
+#else
     auto emit = [&](int c) {
         const int buf = c % NB;
         const int cnt = s_cnt[buf];
@@ -607,6 +655,7 @@ lz4_compress_fast3_kernel(const uint8_t* __restrict__ src_base, const uint64_t* 
         }
         op += total;
     };
+#endif
     auto finish = [&]() {                                  // last literals (lz4.c:1266-1293)
         int ret = 0;
         if (!fail) {
@@ -627,6 +676,9 @@ lz4_compress_fast3_kernel(const uint8_t* __restrict__ src_base, const uint64_t* 
     // ------------------------------------------------------------------ the greedy walk of one chunk (warp P)
     int ip = 0, anchor = 0;
 #if B200_V3_RUNS
+#if B200_V3_SPLIT
+    int pop = 0; bool pfail = false;                       // warp P's own output offset / overflow flag
+#endif
     auto walk = [&](int c) {
         const int cp0 = 128 * c - int(ph), buf = c % NB;
         const bool inner = cp0 >= 4 && cp0 + 128 + 32 <= n;  // every measurement window of this chunk lies inside the block
@@ -744,19 +796,53 @@ lz4_compress_fast3_kernel(const uint8_t* __restrict__ src_base, const uint64_t* 
                 const unsigned below = sel & ((1u << lane) - 1u);
                 int pend = __shfl_sync(B200_FULL, end, (31 - __clz(below)) & 31);     // end of the previous selected sequence
                 if (!below) pend = anchor;
-                if ((sel >> lane) & 1u) {
-                    int start, len;
+                const bool selme = ((sel >> lane) & 1u) != 0;
+                int start = pend, len = 4;
+                if (selme) {
                     if ((msel >> lane) & 1u) { start = pend; len = end - pend; }         // entered inside the run: no catch-up
                     else { const int bk = min(back, ms - pend); start = ms - bk; len = ml + bk; }
-                    s_rec[32 * buf + k + __popc(below)] = make_uint2(uint32_t(start) | (uint32_t(dist) << 16), uint32_t(len));
                 }
+#if B200_V3_SPLIT
+                // lay the headers out here (lz4.c:1094-1100, 1133, 1184-1196); warp L copies the literal bytes later
+                const int lit = selme ? start - pend : 0, mcode = len - 4;
+                const int lhdr = lit >= 15 ? (lit - 15) / 255 + 1 : 0;
+                const int mhdr = (selme && mcode >= 15) ? (mcode - 15) / 255 + 1 : 0;
+                const int size = selme ? 1 + lhdr + lit + 2 + mhdr : 0;
+                int incl = size;
+                #pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(B200_FULL, incl, d); if (lane >= d) incl += y; }
+                const int total = __shfl_sync(B200_FULL, incl, 31);
+                if (!pfail && uint32_t(pop) + uint32_t(total) > uint32_t(cap)) pfail = true;         // lz4.c:1085-1088, 1158
+                if (!pfail) {
+                    const int o = pop + incl - size;
+                    if (selme) {
+                        uint8_t* d = dst + o;
+                        d[0] = uint8_t((min(lit, 15) << 4) | min(mcode, 15));
+                        d += 1;
+                        if (lit >= 15) { int v = lit - 15; for (; v >= 255; v -= 255) *d++ = 255; *d++ = uint8_t(v); }
+                        d += lit;
+                        d[0] = uint8_t(dist); d[1] = uint8_t(dist >> 8);
+                        d += 2;
+                        if (mcode >= 15) { int v = mcode - 15; for (; v >= 255; v -= 255) *d++ = 255; *d++ = uint8_t(v); }
+                        s_rec4[32 * buf + k + __popc(below)] = make_uint4(uint32_t(pend), uint32_t(lit), uint32_t(o + 1 + lhdr), 0u);
+                    }
+                    pop += total;
+                }
+#else
+                if (selme) s_rec[32 * buf + k + __popc(below)] = make_uint2(uint32_t(start) | (uint32_t(dist) << 16), uint32_t(len));
+#endif
                 k += __popc(sel);
                 ip = anchor = __shfl_sync(B200_FULL, end, 31 - __clz(sel));
             }
             if (nh <= 32) break;                             // every run start of the chunk was in this round
             __syncwarp();                                    // s_hit is re-ranked from the new ip
         }
-        if (lane == 0) s_cnt[buf] = k;
+        if (lane == 0) {
+            s_cnt[buf] = k;
+#if B200_V3_SPLIT
+            s_state[4 * buf] = pop; s_state[4 * buf + 1] = anchor; s_state[4 * buf + 2] = int(pfail);
+#endif
+        }
     };
 #else
     auto walk = [&](int c) {
@@ -906,7 +992,7 @@ lz4_compress_fast3_kernel(const uint8_t* __restrict__ src_base, const uint64_t* 
 template <int HASH_LOG, bool SPARSE>
 static cudaError_t launch_v3(const BatchArgs& a, cudaStream_t st)
 {
-    const size_t smem = (2u << HASH_LOG) + B200_V3_NB * (256 + 256 + 16) + 16 + 128 + (B200_V3_RUNS ? B200_V3_NB * 16 : 0);
+    const size_t smem = (2u << HASH_LOG) + B200_V3_NB * (256 + 256 + 16) + 16 + 128 + (B200_V3_RUNS ? B200_V3_NB * 16 : 0) + (B200_V3_SPLIT ? B200_V3_NB * (256 + 16) : 0);
     auto k = lz4_compress_fast3_kernel<HASH_LOG, SPARSE>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;

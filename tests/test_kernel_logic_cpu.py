@@ -383,19 +383,25 @@ def test_host_layer_on_the_emulator_library():
 
 
 # ---------------------------------------------------------------------------------------------- experimental build knobs
-def test_run_start_parser_variant_emits_the_same_bytes(csim, port):
-    """B200_V3_RUNS=1 (DESIGN.md, round-2 plan; off by default, not yet measured): warp P ranks and measures run STARTS only
-    and enters a run in the middle when the previous sequence ends inside it.  It must be the same greedy parse: byte-identical
-    output to the default build for every table variant, full and limited capacity — on the corpus and on shapes made to
-    stress runs (short periods, alternating distances, > 32 run starts per 128-byte chunk)."""
+def test_experimental_parser_variants_emit_the_same_bytes(csim, port):
+    """Compile-time variants of the two-warp fast compressor (DESIGN.md, round-2 plan; off by default, not yet measured):
+      B200_V3_RUNS=1   warp P ranks and measures run STARTS only and enters a run in the middle when the previous sequence
+                       ends inside it;
+      + B200_V3_SPLIT=1  warp P also lays out the sequence headers, warp L only copies literal bytes.
+    Both must be the same greedy parse and layout: byte-identical output to the default build for every table variant, full
+    and limited capacity — on the corpus and on shapes made to stress runs (short periods, alternating distances, more than
+    32 run starts per 128-byte chunk)."""
     out = os.path.join(HERE, "simt", "_build")
-    so = os.path.join(out, "libcompsim_runs.so")
-    subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-Wno-unknown-pragmas", "-Wno-attributes", "-DB200_HOST_SIM",
-                    "-DB200_V3_RUNS=1", "-I" + os.path.join(HERE, "simt"), "-I" + os.path.join(ROOT, "lz4-java_b200", "csrc"),
-                    os.path.join(HERE, "simt", "comp_harness.cpp"), "-o", so], check=True, capture_output=True)
-    runs = ctypes.CDLL(so)
-    runs.sim_compress_fast.restype = ctypes.c_int
-    runs.sim_compress_fast.argtypes = csim.sim_compress_fast.argtypes
+    variants = []
+    for name, flags in (("runs", ["-DB200_V3_RUNS=1"]), ("split", ["-DB200_V3_RUNS=1", "-DB200_V3_SPLIT=1"])):
+        so = os.path.join(out, f"libcompsim_{name}.so")
+        subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-Wno-unknown-pragmas", "-Wno-attributes", "-DB200_HOST_SIM"] + flags +
+                       ["-I" + os.path.join(HERE, "simt"), "-I" + os.path.join(ROOT, "lz4-java_b200", "csrc"),
+                        os.path.join(HERE, "simt", "comp_harness.cpp"), "-o", so], check=True, capture_output=True)
+        lib = ctypes.CDLL(so)
+        lib.sim_compress_fast.restype = ctypes.c_int
+        lib.sim_compress_fast.argtypes = csim.sim_compress_fast.argtypes
+        variants.append((name, lib))
 
     def run(lib, b, cap, hl, sparse):
         s = _src(b); d = np.full(cap + 2 * PAD, 0x55, dtype=np.uint8)
@@ -416,8 +422,11 @@ def test_run_start_parser_variant_emits_the_same_bytes(csim, port):
         for hl, sp in ((13, 0), (12, 0), (13, 1)):
             cap = port.compress_bound(len(d))
             want = run(csim, d, cap, hl, sp)
-            assert run(runs, d, cap, hl, sp) == want, (name, hl, sp)
+            for vn, lib in variants:
+                assert run(lib, d, cap, hl, sp) == want, (vn, name, hl, sp)
             if hl == 13 and sp == 0 and want[0] > 0:
                 assert port.decompress_safe(want[1], len(d)) == (len(d), d), name
                 for cap2 in (want[0] - 1, max(0, want[0] - rng.randrange(2, 40))):
-                    assert run(runs, d, cap2, hl, sp) == run(csim, d, cap2, hl, sp), (name, cap2)
+                    w2 = run(csim, d, cap2, hl, sp)
+                    for vn, lib in variants:
+                        assert run(lib, d, cap2, hl, sp) == w2, (vn, name, cap2)
