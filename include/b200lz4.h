@@ -155,6 +155,9 @@ int b200lz4_compress_fast_compact_host(const uint8_t* src_base, const uint64_t* 
 int b200lz4_compress_fast_batch_host_multi(const uint8_t* src_base, const uint64_t* src_off, const int32_t* src_len,
                                            uint8_t* dst_base, const uint64_t* dst_off, const int32_t* dst_cap,
                                            int32_t* result, size_t n, int max_src_len, const int* devices, int ndev);
+int b200lz4_compress_hc_batch_host_multi(const uint8_t* src_base, const uint64_t* src_off, const int32_t* src_len,
+                                         uint8_t* dst_base, const uint64_t* dst_off, const int32_t* dst_cap,
+                                         int32_t* result, size_t n, int level, const int* devices, int ndev);
 int b200lz4_decompress_safe_batch_host_multi(const uint8_t* src_base, const uint64_t* src_off, const int32_t* src_len,
                                              uint8_t* dst_base, const uint64_t* dst_off, const int32_t* dst_cap,
                                              int32_t* result, size_t n, const int* devices, int ndev);

@@ -107,6 +107,15 @@ def compress_fast_batch_host_multi(src, src_off, src_len, dst, dst_off, dst_cap,
     return res
 
 
+def compress_hc_batch_host_multi(src, src_off, src_len, dst, dst_off, dst_cap, devices, level=9) -> np.ndarray:
+    src_off, src_len, dst_off, dst_cap = _np(src_off, np.uint64), _np(src_len, np.int32), _np(dst_off, np.uint64), _np(dst_cap, np.int32)
+    res = np.zeros(len(src_off), dtype=np.int32)
+    arr, k = _devs(devices)
+    N.check(N.lib().b200lz4_compress_hc_batch_host_multi(_p(src), _p(src_off), _p(src_len), _p(dst), _p(dst_off), _p(dst_cap),
+                                                         _p(res), len(src_off), level, arr, k))
+    return res
+
+
 def decompress_safe_batch_host_multi(src, src_off, src_len, dst, dst_off, dst_cap, devices) -> np.ndarray:
     src_off, src_len, dst_off, dst_cap = _np(src_off, np.uint64), _np(src_len, np.int32), _np(dst_off, np.uint64), _np(dst_cap, np.int32)
     res = np.zeros(len(src_off), dtype=np.int32)

@@ -746,6 +746,10 @@ int b200lz4_compress_fast_batch_host_multi(const uint8_t* src_base, const uint64
                                            uint8_t* dst_base, const uint64_t* dst_off, const int32_t* dst_cap,
                                            int32_t* result, size_t n, int max_src_len, const int* devices, int ndev)
 { return multi_host_batch(OP_COMPRESS_FAST, src_base, src_off, src_len, dst_base, dst_off, dst_cap, result, n, max_src_len, devices, ndev); }
+int b200lz4_compress_hc_batch_host_multi(const uint8_t* src_base, const uint64_t* src_off, const int32_t* src_len,
+                                         uint8_t* dst_base, const uint64_t* dst_off, const int32_t* dst_cap,
+                                         int32_t* result, size_t n, int level, const int* devices, int ndev)
+{ return multi_host_batch(OP_COMPRESS_HC, src_base, src_off, src_len, dst_base, dst_off, dst_cap, result, n, level, devices, ndev); }
 int b200lz4_decompress_safe_batch_host_multi(const uint8_t* src_base, const uint64_t* src_off, const int32_t* src_len,
                                              uint8_t* dst_base, const uint64_t* dst_off, const int32_t* dst_cap,
                                              int32_t* result, size_t n, const int* devices, int ndev)

@@ -834,6 +834,14 @@ def test_multi_gpu_range_sharded_host_batches(b200, checker):
             assert out[o:o + len(d)].tobytes() == d and out2[o:o + len(d)].tobytes() == d, (devs, k)
         assert (b200.batch.xxh32_batch_host_multi(src, soff, slen, devs, 7) == want_h32).all()
         assert (b200.batch.xxh64_batch_host_multi(src, soff, slen, devs, 7) == want_h64).all()
+    # HC: same sharding (a few blocks: one CTA each)
+    hc_want = np.zeros(ctotal, dtype=np.uint8)
+    hc_len = b200.batch.compress_hc_batch_host(src, soff[:6], slen[:6], hc_want, coff[:6], ccap[:6])
+    hc = np.zeros(ctotal, dtype=np.uint8)
+    assert (b200.batch.compress_hc_batch_host_multi(src, soff[:6], slen[:6], hc, coff[:6], ccap[:6], [0, 0]) == hc_len).all()
+    for k in range(6):
+        o = int(coff[k])
+        assert hc[o:o + int(hc_len[k])].tobytes() == hc_want[o:o + int(hc_len[k])].tobytes(), k
     # fewer blocks than devices, no blocks, and a device that does not exist
     two = b200.batch.compress_fast_batch_host_multi(src, soff[:2], slen[:2], np.zeros(ctotal, dtype=np.uint8), coff[:2], ccap[:2], [0] * 5)
     assert (two == want_len[:2]).all()
