@@ -5,6 +5,7 @@
 set -e
 cd "$(dirname "$0")/../lz4-java_b200/csrc"
 make -j8 >/dev/null
+mkdir -p ../../variants
 ARCH="-gencode arch=compute_100a,code=sm_100a"
 for spec in "$@"; do
   name="${spec%%:*}"; flags="${spec#*:}"

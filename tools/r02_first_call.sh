@@ -17,8 +17,6 @@ timeout 1200 python -m pytest tests -m gpu -q -W ignore::DeprecationWarning > $O
 B200_EXPERIMENTAL=1 timeout 600 python -m pytest tests -m gpu -q -W ignore::DeprecationWarning -k "hc" > $O/gpu_tests_experimental.log 2>&1; tail -2 $O/gpu_tests_experimental.log | cut -c1-300
 timeout 900 python bench.py --impl reference > $O/bench_reference_arm.json 2> $O/bench_reference.err; tail -c 300 $O/bench_reference_arm.json
 timeout 1500 python bench.py > $O/bench_full.json 2> $O/bench_full.err; tail -c 600 $O/bench_full.json
-B200_EXPERIMENTAL=1 timeout 1500 python tools/bench_configs.py > $O/secondary_configs.log 2>&1; tail -12 $O/secondary_configs.log | cut -c1-300
-for mb in 64 128 512; do B200LZ4_CHUNK_MB=$mb timeout 300 python tools/e2e_probe.py 2>&1 | head -3 | cut -c1-300; done > $O/e2e_chunk_sweep.log 2>&1; cat $O/e2e_chunk_sweep.log
 # 6. A/B of the run-start parser (B200_V3_RUNS=1: same bytes, fewer measurements; DESIGN.md round-2 plan), three corpora
 bash tools/build_variants.sh runs:"-DB200_V3_RUNS=1" split:"-DB200_V3_RUNS=1 -DB200_V3_SPLIT=1" > $O/variant_build.log 2>&1
 for mp in 0.5 0.8 0.2; do
@@ -30,5 +28,7 @@ M=gpu__time_duration.sum,smsp__inst_executed.sum,smsp__issue_active.avg.pct_of_p
 for so in lz4-java_b200/libb200lz4.so variants/libb200lz4_runs.so variants/libb200lz4_split.so; do
   B200LZ4_TEST_SO=$so NBLK=8192 VARIANTS=13:0:3:0 timeout 600 ncu --metrics $M --clock-control none -k regex:lz4_compress_fast3 -s 2 -c 1 --csv --log-file $O/runs_ab_$(basename $so .so).csv python tools/probe.py > /dev/null 2>&1
 done
+B200_EXPERIMENTAL=1 timeout 1500 python tools/bench_configs.py > $O/secondary_configs.log 2>&1; tail -12 $O/secondary_configs.log | cut -c1-300
+for mb in 64 128 512; do B200LZ4_CHUNK_MB=$mb timeout 300 python tools/e2e_probe.py 2>&1 | head -3 | cut -c1-300; done > $O/e2e_chunk_sweep.log 2>&1; cat $O/e2e_chunk_sweep.log
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/bench_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu > $O/bench_under_ncu.log 2>&1
 ls -la $O
