@@ -92,3 +92,62 @@ def pack(items, align=1, pad=0):
     for o, it in zip(offs, items):
         buf[o:o + len(it)] = np.frombuffer(it, dtype=np.uint8)
     return buf, np.array(offs, dtype=np.uint64), np.array(lens, dtype=np.int32)
+
+
+# ---- fixtures and data recipes of the reference's own tests
+def issue12():
+    """the regression input of https://github.com/jpountz/lz4-java/issues/12 as LZ4Test.java:488-539 uses it: bytes [9:] of
+    the array literal (committed under tests/golden/issue12.json, extracted once from the reference's test source)"""
+    import json
+    raw = bytes.fromhex(json.load(open(os.path.join(HERE, "golden", "issue12.json")))["hex"])
+    return raw[9:]
+
+
+class JavaRandom:
+    """java.util.Random (the 48-bit LCG of the Java SE specification), enough of it to rebuild the test data of
+    LZ4FrameIOStreamTest.java: nextInt() and nextBytes()"""
+
+    def __init__(self, seed: int):
+        self.s = (seed ^ 0x5DEECE66D) & ((1 << 48) - 1)
+
+    def next(self, bits: int) -> int:
+        self.s = (self.s * 0x5DEECE66D + 0xB) & ((1 << 48) - 1)
+        v = self.s >> (48 - bits)
+        return v - (1 << bits) if v >= (1 << (bits - 1)) else v        # signed, like Java's int
+
+    def next_int(self) -> int:
+        return self.next(32)
+
+    def next_bytes(self, n: int) -> bytes:
+        out = bytearray()
+        while len(out) < n:
+            rnd = self.next_int() & 0xFFFFFFFF
+            for _ in range(min(n - len(out), 4)):
+                out.append(rnd & 0xFF); rnd >>= 8
+        return bytes(out)
+
+
+def frame_test_sizes():
+    """LZ4FrameIOStreamTest.java:73-90: the fixed sizes + ten drawn from Random(78370789134L)"""
+    sizes = [0, 1, 1 << 10, (1 << 10) + 1, 1 << 16, 1 << 17, 1 << 20]
+    rnd = JavaRandom(78370789134)
+    for _ in range(10):
+        v = rnd.next_int()
+        sizes.append(abs(v) % (1 << 22))                                 # Math.abs(rnd.nextInt()) % (1 << 22)
+    return sizes
+
+
+def frame_test_data(size: int) -> bytes:
+    """LZ4FrameIOStreamTest.java:100-119: 1 KiB buffers of Random(5378L).nextBytes whose whole 32-bit words are then
+    overwritten with 0xDEADBEEF (little-endian) — so only a final partial word keeps random bytes"""
+    rnd = JavaRandom(5378)
+    out = bytearray()
+    remaining = size
+    while remaining > 0:
+        n = min(remaining, 1 << 10)
+        buf = bytearray(rnd.next_bytes(n))
+        for w in range(n // 4):
+            buf[4 * w:4 * w + 4] = b"\xEF\xBE\xAD\xDE"
+        out += buf
+        remaining -= n
+    return bytes(out)

@@ -938,3 +938,28 @@ def test_streaming_hash_past_4gb(b200, port):
             assert h32.getValue() == L.orc_xxh32_digest(s32) == h32.getValue(), total
             assert h64.getValue() == L.orc_xxh64_digest(s64) == h64.getValue(), total
     h32.close(); h64.close()
+
+
+def test_reference_test_fixtures_on_gpu(b200, port):
+    """LZ4Test.testRoundtripIssue12 (the array at offset 9, LZ4Test.java:488-539) with the fast and the HC compressor, and
+    the LZ4FrameIOStreamTest data recipe at all 17 of its sizes through the frame writer / reader and the LZ4Block
+    container, each checked against the CPU checker in both directions"""
+    import json
+    raw = bytes.fromhex(json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "issue12.json")))["hex"])
+    d = corpus.issue12()
+    f = b200.LZ4Factory.b200Instance()
+    for comp in (f.fastCompressor(), f.highCompressor(9)):
+        dest = bytearray(comp.maxCompressedLength(len(d)) + 5)
+        n = comp.compress(raw, 9, len(raw) - 9, dest, 5, len(dest) - 5)          # testRoundTrip(data, 9, data.length - 9)
+        c = bytes(dest[5:5 + n])
+        assert port.decompress_safe(c, len(d)) == (len(d), d)
+        assert f.safeDecompressor().decompress(c, maxDestLen=len(d)) == d
+        assert f.fastDecompressor().decompress(c, destLen=len(d)) == d
+    for k, n in enumerate(corpus.frame_test_sizes()):
+        data = corpus.frame_test_data(n)
+        flags = (1, 0, 3, 7, 5)[k % 5]
+        assert b200.decompress_frames(port.frame_compress(data, 4 + k % 4, flags), n + 8) == data, n
+        fr = b200.compress_frame(data, 4 + (k + 1) % 4, content_checksum=bool(flags & 1), block_checksum=bool(flags & 2), content_size=bool(flags & 4))
+        assert port.frame_decompress(fr, n + 8) == (n, data), n
+        if n <= (1 << 20):
+            assert b200.decompress_lz4block(b200.compress_lz4block(data, 1 << 16), n + 8) == data, n

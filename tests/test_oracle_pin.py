@@ -198,3 +198,22 @@ def test_java_port_restatement_cross_checks(port):
         assert port.java_decompress_safe(v, 20)[0] < 0 and port.decompress_safe(v, 20)[0] < 0, v.hex()
         for n in (10, 20):
             assert port.java_decompress_fast(v, n)[0] < 0 and port.decompress_fast(v + bytes(32), n)[0] < 0, (v.hex(), n)
+
+
+def test_reference_test_fixtures_on_the_checkers(port):
+    """the reference's own fixed inputs: the issue-#12 regression array (LZ4Test.java:488-539) through both restated
+    compressors and all restated decoders, and the frame test data of LZ4FrameIOStreamTest.java:73-119 (sizes from
+    Random(78370789134L), bytes from Random(5378L) overwritten with 0xDEADBEEF words) through the frame container"""
+    d = corpus.issue12()
+    assert len(d) == 1510
+    for c in (port.compress(d), port.java_compress(d)):
+        assert port.decompress_safe(c, len(d)) == (len(d), d) and port.java_decompress_safe(c, len(d)) == (len(d), d)
+        assert port.decompress_fast(c + bytes(8), len(d)) == (len(c), d)
+    sizes = corpus.frame_test_sizes()
+    assert sizes[:7] == [0, 1, 1 << 10, (1 << 10) + 1, 1 << 16, 1 << 17, 1 << 20] and len(sizes) == 17 and all(0 <= s < (1 << 22) for s in sizes)
+    assert corpus.JavaRandom(42).next_int() == -1170105035                   # java.util.Random's documented sequence
+    for n in sizes[:8]:
+        data = corpus.frame_test_data(n)
+        assert len(data) == n and data[:n // 4 * 4] == b"\xEF\xBE\xAD\xDE" * (n // 4)
+        for flags in (0, 1, 7):
+            assert port.frame_decompress(port.frame_compress(data, 4, flags), n + 8) == (n, data)
