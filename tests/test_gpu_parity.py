@@ -434,6 +434,10 @@ def test_xxhash_streaming(b200, checker):
             want = checker.xxh32(data, seed) if bits == 32 else checker.xxh64(data, seed)
             assert h.getValue() == want
             h.close()
+            h.close()                                  # XXHash32Test.java:167-190 (testClose): closing twice is fine,
+            for use in (h.getValue, h.reset, lambda: h.update(b"x")):     # any use afterwards is an AssertionError
+                with pytest.raises(AssertionError):
+                    use()
 
 
 def test_factory_api_contract(b200, checker):
