@@ -32,3 +32,7 @@ B200_EXPERIMENTAL=1 timeout 1500 python tools/bench_configs.py > $O/secondary_co
 for mb in 64 128 512; do B200LZ4_CHUNK_MB=$mb timeout 300 python tools/e2e_probe.py 2>&1 | head -3 | cut -c1-300; done > $O/e2e_chunk_sweep.log 2>&1; cat $O/e2e_chunk_sweep.log
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/bench_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu > $O/bench_under_ncu.log 2>&1
 ls -la $O
+
+# Multi-GPU follow-up (separate call, N GPUs of one box):
+#   /usr/local/graft/bin/gpurun --gpus 2 --timeout 900 -- 'NBLK=65536 python tools/e2e_multi_probe.py > gpurun_out/e2e_multi.log 2>&1; \
+#       python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 > gpurun_out/bench_2gpu.json'
