@@ -164,6 +164,16 @@ int b200lz4_decompress_safe_batch_host_multi(const uint8_t* src_base, const uint
 int b200lz4_decompress_fast_batch_host_multi(const uint8_t* src_base, const uint64_t* src_off, const int32_t* src_avail,
                                              uint8_t* dst_base, const uint64_t* dst_off, const int32_t* dst_len,
                                              int32_t* result, size_t n, const int* devices, int ndev);
+/* Packed output from several GPUs: shard g's compressed blocks are packed back to back (like
+ * b200lz4_compress_fast_compact_host) starting at dst_base + shard_base[g], where shard_base[g] is the sum of the 16-byte
+ * aligned bounds of the blocks before the shard — known before anything is compressed, so the GPUs never wait for each
+ * other.  out_off[i] is absolute in dst_base; shard_total[g] = packed bytes of shard g.  The stream is contiguous within a
+ * shard and has a gap between shards: a caller writes the ndev pieces one after the other (gather write).  dst_capacity
+ * must hold the aligned bounds of all blocks.  shard_base / shard_total: ndev entries each (may be NULL). */
+int b200lz4_compress_fast_compact_host_multi(const uint8_t* src_base, const uint64_t* src_off, const int32_t* src_len,
+                                             uint8_t* dst_base, size_t dst_capacity, uint64_t* out_off,
+                                             int32_t* result, size_t n, int max_src_len, const int* devices, int ndev,
+                                             uint64_t* shard_base, uint64_t* shard_total);
 int b200xxh32_batch_host_multi(const uint8_t* base, const uint64_t* off, const int32_t* len, uint32_t seed,
                                uint32_t* out, size_t n, const int* devices, int ndev);
 int b200xxh64_batch_host_multi(const uint8_t* base, const uint64_t* off, const int32_t* len, uint64_t seed,

@@ -55,6 +55,7 @@ SYMBOLS = [
     ("b200xxh32_batch_host", _i, [_vp, _vp, _vp, _u32, _vp, _sz]),
     ("b200xxh64_batch_host", _i, [_vp, _vp, _vp, _u64, _vp, _sz]),
     ("b200lz4_compress_fast_batch_host_multi", _i, _BATCH + [_i, _vp, _i]),
+    ("b200lz4_compress_fast_compact_host_multi", _i, [_vp, _vp, _vp, _vp, _sz, _vp, _vp, _sz, _i, _vp, _i, _vp, _vp]),
     ("b200lz4_compress_hc_batch_host_multi", _i, _BATCH + [_i, _vp, _i]),
     ("b200lz4_decompress_safe_batch_host_multi", _i, _BATCH + [_vp, _i]),
     ("b200lz4_decompress_fast_batch_host_multi", _i, _BATCH + [_vp, _i]),

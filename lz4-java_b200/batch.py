@@ -107,6 +107,19 @@ def compress_fast_batch_host_multi(src, src_off, src_len, dst, dst_off, dst_cap,
     return res
 
 
+def compress_fast_compact_host_multi(src, src_off, src_len, dst, devices, max_src_len=0):
+    """-> (out_off[u64] absolute in dst, out_len[i32], shard_base[u64], shard_total[u64]): packed within each GPU's shard"""
+    src_off, src_len = _np(src_off, np.uint64), _np(src_len, np.int32)
+    n = len(src_off)
+    out_off = np.zeros(n, dtype=np.uint64)
+    res = np.zeros(n, dtype=np.int32)
+    arr, k = _devs(devices)
+    sbase, stotal = np.zeros(max(k, 1), dtype=np.uint64), np.zeros(max(k, 1), dtype=np.uint64)
+    N.check(N.lib().b200lz4_compress_fast_compact_host_multi(_p(src), _p(src_off), _p(src_len), _p(dst), dst.nbytes, _p(out_off),
+                                                             _p(res), n, max_src_len, arr, k, _p(sbase), _p(stotal)))
+    return out_off, res, sbase, stotal
+
+
 def compress_hc_batch_host_multi(src, src_off, src_len, dst, dst_off, dst_cap, devices, level=9) -> np.ndarray:
     src_off, src_len, dst_off, dst_cap = _np(src_off, np.uint64), _np(src_len, np.int32), _np(dst_off, np.uint64), _np(dst_cap, np.int32)
     res = np.zeros(len(src_off), dtype=np.int32)

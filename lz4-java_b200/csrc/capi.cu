@@ -758,6 +758,39 @@ int b200lz4_decompress_fast_batch_host_multi(const uint8_t* src_base, const uint
                                              uint8_t* dst_base, const uint64_t* dst_off, const int32_t* dst_len,
                                              int32_t* result, size_t n, const int* devices, int ndev)
 { return multi_host_batch(OP_DEC_FAST, src_base, src_off, src_avail, dst_base, dst_off, dst_len, result, n, 0, devices, ndev); }
+int b200lz4_compress_fast_compact_host_multi(const uint8_t* src_base, const uint64_t* src_off, const int32_t* src_len,
+                                             uint8_t* dst_base, size_t dst_capacity, uint64_t* out_off,
+                                             int32_t* result, size_t n, int max_src_len, const int* devices, int ndev,
+                                             uint64_t* shard_base, uint64_t* shard_total)
+{
+    if (ndev < 1 || ndev > 64) return fail_arg("ndev must be 1..64");
+    for (int g = 0; g < ndev; g++) { if (shard_base) shard_base[g] = 0; if (shard_total) shard_total[g] = 0; }
+    if (n == 0) return 0;
+    if (!src_base || !src_off || !src_len || !dst_base || !out_off || !result) return fail_arg("null pointer");
+    // region of shard g: the aligned bounds of its blocks, laid end to end (prefix sums at the shard boundaries only)
+    std::vector<uint64_t> base((size_t)ndev + 1, 0);
+    {
+        uint64_t acc = 0; int g = 0;
+        for (size_t i = 0; i <= n; i++) {
+            while (g <= ndev && i == n * (size_t)g / (size_t)ndev) base[(size_t)g++] = acc;
+            if (i < n) { const uint64_t len = (uint64_t)(src_len[i] > 0 ? src_len[i] : 0); acc += ((len + len / 255 + 16) + 15) & ~uint64_t(15); }
+        }
+        if (acc > dst_capacity) return fail_arg("dst_capacity must hold the aligned bounds of all blocks");
+    }
+    return run_sharded(n, devices, ndev, [&](size_t lo, size_t cnt) {
+        int g = 0;
+        while (n * (size_t)(g + 1) / (size_t)ndev <= lo) g++;                  // which shard this range is
+        uint64_t total = 0;
+        int rc = b200lz4_compress_fast_compact_host(src_base, src_off + lo, src_len + lo, dst_base + base[(size_t)g],
+                                                    (size_t)(base[(size_t)g + 1] - base[(size_t)g]), out_off + lo, result + lo, cnt,
+                                                    max_src_len, &total);
+        if (rc) return rc;
+        for (size_t i = lo; i < lo + cnt; i++) out_off[i] += base[(size_t)g];
+        if (shard_base) shard_base[g] = base[(size_t)g];
+        if (shard_total) shard_total[g] = total;
+        return 0;
+    });
+}
 int b200xxh32_batch_host_multi(const uint8_t* base, const uint64_t* off, const int32_t* len, uint32_t seed,
                                uint32_t* out, size_t n, const int* devices, int ndev)
 {

@@ -838,6 +838,22 @@ def test_multi_gpu_range_sharded_host_batches(b200, checker):
             assert out[o:o + len(d)].tobytes() == d and out2[o:o + len(d)].tobytes() == d, (devs, k)
         assert (b200.batch.xxh32_batch_host_multi(src, soff, slen, devs, 7) == want_h32).all()
         assert (b200.batch.xxh64_batch_host_multi(src, soff, slen, devs, 7) == want_h64).all()
+    # packed output per shard: same bytes as the single-GPU compaction, shard by shard, at bases known in advance
+    pk = np.zeros(ctotal, dtype=np.uint8)
+    w_off, w_len, w_total = b200.batch.compress_fast_compact_host(src, soff, slen, pk)
+    for devs in lists:
+        nd = devs if isinstance(devs, int) else len(devs)
+        pm = np.full(ctotal, 0x77, dtype=np.uint8)
+        ooff, olen, sbase, stotal = b200.batch.compress_fast_compact_host_multi(src, soff, slen, pm, devs)
+        assert (olen == w_len).all() and int(stotal.sum()) == w_total, devs
+        for g in range(nd):
+            lo, hi = len(datas) * g // nd, len(datas) * (g + 1) // nd
+            want = b"".join(pk[int(w_off[i]):int(w_off[i]) + int(w_len[i])].tobytes() for i in range(lo, hi))
+            assert int(stotal[g]) == len(want) and pm[int(sbase[g]):int(sbase[g]) + len(want)].tobytes() == want, (devs, g)
+            if hi > lo:
+                assert int(ooff[lo]) == int(sbase[g]), (devs, g)
+    with pytest.raises(b200.B200Error, match="dst_capacity"):
+        b200.batch.compress_fast_compact_host_multi(src, soff, slen, np.zeros(1000, dtype=np.uint8), [0, 0])
     # HC: same sharding (a few blocks: one CTA each)
     hc_want = np.zeros(ctotal, dtype=np.uint8)
     hc_len = b200.batch.compress_hc_batch_host(src, soff[:6], slen[:6], hc_want, coff[:6], ccap[:6])
