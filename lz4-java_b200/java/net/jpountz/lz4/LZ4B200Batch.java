@@ -44,6 +44,27 @@ public final class LZ4B200Batch {
     return out;
   }
 
+  /** What {@link #compressPacked} returns: per-block offsets (absolute in dst) and sizes, and the packed piece of each GPU. */
+  public static final class Packed {
+    public final long[] offset; public final int[] length; public final long[] shardBase; public final long[] shardLength;
+    Packed(long[] o, int[] l, long[] b, long[] t) { offset = o; length = l; shardBase = b; shardLength = t; }
+  }
+
+  /** Compresses n equally sized blocks on {@code gpus} devices and packs each device's blocks back to back in dst (only
+   *  compressed bytes cross PCIe).  The pieces [shardBase[g], shardBase[g] + shardLength[g]) written one after the other
+   *  are the packed stream; dst must hold n slots of maxCompressedLength(blockSize) rounded up to 16. */
+  public static Packed compressPacked(ByteBuffer src, int blockSize, int n, ByteBuffer dst, int gpus) {
+    final LongBuffer so = longs(n), oo = longs(n), sb = longs(gpus), st = longs(gpus);
+    final IntBuffer sl = ints(n), res = ints(n);
+    for (int i = 0; i < n; i++) { so.put(i, (long) i * blockSize); sl.put(i, blockSize); }
+    final int rc = LZ4B200JNI.compressPackedMulti(src, so, sl, dst, oo, res, n, blockSize, null, gpus, sb, st);
+    if (rc != 0) throw new LZ4Exception("B200 backend error " + rc);
+    final long[] off = new long[n]; final int[] len = new int[n]; final long[] base = new long[gpus]; final long[] tot = new long[gpus];
+    oo.get(off); res.get(len); sb.get(base); st.get(tot);
+    for (int r : len) if (r <= 0) throw new LZ4Exception("maxDestLen is too small");
+    return new Packed(off, len, base, tot);
+  }
+
   /** Inverse of the sharded {@link #compressUniform(ByteBuffer, int, int, ByteBuffer, int)}. */
   public static void decompressUniform(ByteBuffer src, int[] compressedLen, int blockSize, ByteBuffer dst, int gpus) {
     final int n = compressedLen.length;

@@ -34,6 +34,8 @@ enum LZ4B200JNI {
   static native int compressBatchMulti(ByteBuffer src, LongBuffer srcOff, IntBuffer srcLen, ByteBuffer dst, LongBuffer dstOff, IntBuffer dstCap, IntBuffer result, int n, int maxSrcLen, IntBuffer devices, int ndev);
   static native int decompressFastBatchMulti(ByteBuffer src, LongBuffer srcOff, IntBuffer srcAvail, ByteBuffer dst, LongBuffer dstOff, IntBuffer dstLen, IntBuffer result, int n, IntBuffer devices, int ndev);
   static native int decompressSafeBatchMulti(ByteBuffer src, LongBuffer srcOff, IntBuffer srcLen, ByteBuffer dst, LongBuffer dstOff, IntBuffer dstCap, IntBuffer result, int n, IntBuffer devices, int ndev);
+  /** packed output per GPU shard: shard g's blocks back to back from dst[shardBase[g]], shardTotal[g] bytes; outOff absolute */
+  static native int compressPackedMulti(ByteBuffer src, LongBuffer srcOff, IntBuffer srcLen, ByteBuffer dst, LongBuffer outOff, IntBuffer result, int n, int maxSrcLen, IntBuffer devices, int ndev, LongBuffer shardBase, LongBuffer shardTotal);
   static native int deviceCount();
   static native int registerDirectBuffer(ByteBuffer buf);
 }

@@ -158,6 +158,18 @@ JNIEXPORT jint JNICALL Java_net_jpountz_lz4_LZ4B200JNI_decompressSafeBatchMulti
         (const uint64_t*)(*env)->GetDirectBufferAddress(env, dstOff), (const int32_t*)(*env)->GetDirectBufferAddress(env, dstCap),
         (int32_t*)(*env)->GetDirectBufferAddress(env, result), (size_t)n, device_list(env, devices), ndev);
 }
+/* packed output per GPU shard (b200lz4_compress_fast_compact_host_multi): outOff / shardBase / shardTotal are direct LongBuffers */
+JNIEXPORT jint JNICALL Java_net_jpountz_lz4_LZ4B200JNI_compressPackedMulti
+  (JNIEnv* env, jclass cls, jobject src, jobject srcOff, jobject srcLen, jobject dst, jobject outOff, jobject result, jint n,
+   jint maxSrcLen, jobject devices, jint ndev, jobject shardBase, jobject shardTotal)
+{
+    return b200lz4_compress_fast_compact_host_multi(
+        (const uint8_t*)(*env)->GetDirectBufferAddress(env, src), (const uint64_t*)(*env)->GetDirectBufferAddress(env, srcOff),
+        (const int32_t*)(*env)->GetDirectBufferAddress(env, srcLen), (uint8_t*)(*env)->GetDirectBufferAddress(env, dst),
+        (size_t)(*env)->GetDirectBufferCapacity(env, dst), (uint64_t*)(*env)->GetDirectBufferAddress(env, outOff),
+        (int32_t*)(*env)->GetDirectBufferAddress(env, result), (size_t)n, maxSrcLen, device_list(env, devices), ndev,
+        (uint64_t*)(*env)->GetDirectBufferAddress(env, shardBase), (uint64_t*)(*env)->GetDirectBufferAddress(env, shardTotal));
+}
 JNIEXPORT jint JNICALL Java_net_jpountz_lz4_LZ4B200JNI_deviceCount(JNIEnv* env, jclass cls)
 { (void)env; (void)cls; return b200lz4_device_count(); }
 JNIEXPORT jint JNICALL Java_net_jpountz_lz4_LZ4B200JNI_registerDirectBuffer(JNIEnv* env, jclass cls, jobject buf)
