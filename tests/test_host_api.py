@@ -99,3 +99,32 @@ def test_frame_boundaries_and_byte_balanced_frame_shards(port):
     for bad in (stream[:-3], b"\x01\x02\x03\x04" + stream, stream[:bounds[2][0] + 5]):
         with pytest.raises((EOFError, IOError)):
             frame_boundaries(bad)
+
+
+def test_bench_host_helpers(monkeypatch):
+    """bench.py cannot run here (no GPU), but its host-side sizing logic can: thread counts tried for the CPU legs under a
+    cgroup quota, and the memory room the e2e leg sizes its pinned buffers by"""
+    import importlib
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    bench = importlib.import_module("bench")
+    monkeypatch.setattr(bench, "cpu_threads", lambda: 128)
+    monkeypatch.setattr(bench, "cpu_quota", lambda: "1600000 100000")
+    assert bench.quota_cpus() == 16 and bench.thread_candidates() == [128, 64, 32, 16]
+    monkeypatch.setattr(bench, "cpu_quota", lambda: "max 100000")
+    assert bench.quota_cpus() is None and bench.thread_candidates() == [128, 64]
+    monkeypatch.setattr(bench, "cpu_quota", lambda: "-1")
+    assert bench.thread_candidates() == [128, 64]
+    monkeypatch.setattr(bench, "cpu_quota", lambda: None)
+    assert bench.thread_candidates() == [128, 64]
+    monkeypatch.setattr(bench, "cpu_threads", lambda: 8)
+    monkeypatch.setattr(bench, "cpu_quota", lambda: "1600000 100000")
+    assert bench.thread_candidates() == [8, 4]                      # quota above the visible CPUs: nothing to add
+    room = bench.host_memory_budget()
+    assert room is None or room > (1 << 28)
+    # the bench arms keep the contract's keys
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py")).read()
+    for key in ('"metric"', '"value"', '"unit"', '"n_gpus"', '"ms_per_step"', '"higher_is_better"', '"scaling"', '"vs_baseline"', '"dtype"',
+                '"roofline"', '"cpu_baseline"', '"e2e"', '"gpu_launches"', '"clocks"', '"h2d_bytes_per_step"', '"d2h_bytes_per_step"', '"impl": "reference"'):
+        assert key in src, key
