@@ -18,7 +18,7 @@
 namespace b200 {
 
 static std::atomic<unsigned long long> g_launches{0};
-unsigned long long g_launch_count = 0;      // launches made by frame.cu (single-threaded per call)
+std::atomic<unsigned long long> g_launch_count{0};      // launches made by frame.cu / containers.cu
 static thread_local char tl_err[256] = "";
 static thread_local int tl_status = 0;          // B200LZ4_E_* of the last value-returning call (hashes, digests) on this thread
 static thread_local int tl_device = -1;          // -1: not chosen yet (defaults to device 0)
@@ -807,7 +807,7 @@ int b200xxh64_batch_host_multi(const uint8_t* base, const uint64_t* off, const i
 }
 
 int b200lz4_context_count(void) { return g_contexts.load(std::memory_order_relaxed); }
-uint64_t b200lz4_launch_count(void) { return g_launches.load(std::memory_order_relaxed) + g_launch_count; }
-void     b200lz4_launch_count_reset(void) { g_launches.store(0, std::memory_order_relaxed); g_launch_count = 0; }
+uint64_t b200lz4_launch_count(void) { return g_launches.load(std::memory_order_relaxed) + g_launch_count.load(std::memory_order_relaxed); }
+void     b200lz4_launch_count_reset(void) { g_launches.store(0, std::memory_order_relaxed); g_launch_count.store(0, std::memory_order_relaxed); }
 
 } // extern "C"

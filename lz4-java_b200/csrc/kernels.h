@@ -1,5 +1,6 @@
 // kernels.h — internal launch interface between the C-ABI layer (capi.cu) and the kernels.
 #pragma once
+#include <atomic>
 #include <cstddef>
 #include <cstdint>
 #ifdef B200_HOST_SIM
@@ -49,6 +50,6 @@ cudaError_t launch_xxh64_long(const uint8_t* base, const uint64_t* off, const in
 cudaError_t launch_compact(const uint8_t* slots, const uint64_t* slot_off, const int32_t* lens,
                            uint8_t* out, uint64_t* out_off, uint64_t* total, size_t n, cudaStream_t st);
 
-extern unsigned long long g_launch_count;
+extern std::atomic<unsigned long long> g_launch_count;      // launches made outside capi.cu (frame / container calls, any thread)
 
 } // namespace b200
