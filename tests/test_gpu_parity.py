@@ -813,6 +813,8 @@ def test_multi_gpu_range_sharded_host_batches(b200, checker):
     ndev = lib.b200lz4_device_count()
     assert ndev >= 1
     lists = [1, [0, 0, 0], [0] * 7] + ([ndev, list(range(ndev))[::-1]] if ndev > 1 else [])
+    if "sim" in os.environ.get("B200LZ4_TEST_SO", ""):          # emulator build (CPU suite): every launch costs seconds
+        lists = [[0, 0, 0]] + ([list(range(ndev))[::-1]] if ndev > 1 else [])
     datas = [checker.datagen(rng_n, 0.5, 0.0, s).tobytes() for s, rng_n in enumerate([65536, 1, 0, 40000, 65536, 13, 70000, 5000, 65536, 300, 12, 65536, 100000])]
     src, soff, slen = corpus.pack(datas)
     coff, ccap, ctotal = _slots([b200.max_compressed_length(len(d)) for d in datas])
