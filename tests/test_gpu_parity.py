@@ -693,7 +693,7 @@ def test_contexts_are_reused_across_threads(b200, checker):
         t = threading.Thread(target=work, args=(k,)); t.start(); t.join()
         time.sleep(0.05)                     # join() returns before the OS thread has run its thread-exit hooks
     assert not errs, errs
-    assert base + 1 <= lib.b200lz4_context_count() <= base + 3
+    assert base <= lib.b200lz4_context_count() <= base + 3      # (0 new ones if earlier tests left idle contexts in the pool)
     ts = [threading.Thread(target=work, args=(k,)) for k in range(4)]    # four at once: at most four contexts alive
     for t in ts: t.start()
     for t in ts: t.join()
