@@ -19,7 +19,7 @@ from oracle import oracle as O
 
 def main():
     seed, budget = int(sys.argv[1]), float(sys.argv[2])
-    assert "sim" in os.environ.get("B200LZ4_TEST_SO", ""), "meant for the emulator build"
+    assert "sim" in os.environ.get("B200LZ4_TEST_SO", ""), "meant for the emulator build (or its sanitizer twin)"
     rng = random.Random(seed)
     port = O.Port()
     B = L.batch
