@@ -25,6 +25,7 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "lz4_emit.cuh"
+#include "lz4_compress_wide.cuh"
 #include <type_traits>
 #include <algorithm>
 
@@ -1296,6 +1297,22 @@ static cudaError_t launch_v4(const BatchArgs& a, cudaStream_t st)
     return cudaSuccess;
 }
 
+template <int HASH_LOG, int NB, int NW>
+static cudaError_t launch_v5(const BatchArgs& a, cudaStream_t st)
+{
+    constexpr int S = 2;                                                     // sub-rounds of 128 positions per chunk
+    using LY = WideLayout<S, NB, NW>;
+    const size_t smem = LY::smem(HASH_LOG);
+    constexpr int FIT = 233472 / (int(LY::smem(HASH_LOG)) + 1024);          // CTAs per SM that shared memory allows
+    constexpr int MINB = FIT < 16 ? FIT : 16;
+    auto k = lz4_compress_wide_kernel<HASH_LOG, S, NB, NW, MINB>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    cudaFuncSetAttribute(k, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    k<<<(unsigned)a.n, 32 * NW, smem, st>>>(a.src_base, a.src_off, a.src_len, a.dst_base, a.dst_off, a.dst_cap, a.result, (uint32_t)a.n);
+    return cudaGetLastError();
+}
+
 template <int HASH_LOG, bool U16, bool STAGE>
 static cudaError_t launch_variant(const BatchArgs& a, cudaStream_t st)
 {
@@ -1316,12 +1333,19 @@ int b200lz4_compress_hash_log = 13;   // 13 = the reference's table size for <64
 int b200lz4_compress_stage = 0;       // 1 = stage <=64 KiB blocks in shared memory via TMA (v1 parser only)
 int b200lz4_compress_sparse = 0;      // 1 = publish one position in four (pairs with hash_log 12: the 'fast' operating point)
 int b200lz4_compress_algo = 3;        // 3 = decoupled, two-warp pipeline (default); 2 = decoupled, one warp; 1 = coupled warp parser
+int b200lz4_compress_wide = 222;      // algo 5: 100 * warps + 10 * sub-rounds per chunk + chunk buffers
 }
 
 cudaError_t launch_compress_fast(const BatchArgs& a, int max_src_len, cudaStream_t st)
 {
     if (a.n == 0) return cudaSuccess;
     const bool u16 = max_src_len > 0 && max_src_len <= 65536;
+    if (b200lz4_compress_algo == 5 && u16) {
+        switch (b200lz4_compress_wide) {               // 100 * warps + 20 + chunk buffers
+        case 322: return launch_v5<13, 2, 3>(a, st);
+        default: return launch_v5<13, 2, 2>(a, st);
+        }
+    }
     if (b200lz4_compress_algo == 4 && !b200lz4_compress_stage && u16) {
         if (b200lz4_compress_hash_log == 12) return b200lz4_compress_sparse ? launch_v4<12, true>(a, st) : launch_v4<12, false>(a, st);
         return b200lz4_compress_sparse ? launch_v4<13, true>(a, st) : launch_v4<13, false>(a, st);

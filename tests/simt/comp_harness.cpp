@@ -9,7 +9,10 @@ extern "C" int sim_compress_fast(const uint8_t* src, int n, uint8_t* dst, int ca
 {
     uint64_t zero = 0; int32_t sl = n, dc = cap, res = 0x7FFFFFFF;
 #define ARGS src, &zero, &sl, dst, &zero, &dc, &res, 1u
-    if (algo == 3) {
+    if (algo == 5) {          // stage = 100 * warps + 20 + chunk buffers
+        if (stage == 322) simt::launch(1, 96, [&] { lz4_compress_wide_kernel<13, 2, 2, 3, 1>(ARGS); });
+        else simt::launch(1, 64, [&] { lz4_compress_wide_kernel<13, 2, 2, 2, 1>(ARGS); });
+    } else if (algo == 3) {
         if (hash_log == 12) { if (sparse) simt::launch(1, 64, [&] { lz4_compress_fast3_kernel<12, true>(ARGS); }); else simt::launch(1, 64, [&] { lz4_compress_fast3_kernel<12, false>(ARGS); }); }
         else                { if (sparse) simt::launch(1, 64, [&] { lz4_compress_fast3_kernel<13, true>(ARGS); }); else simt::launch(1, 64, [&] { lz4_compress_fast3_kernel<13, false>(ARGS); }); }
     } else if (algo == 2) {

@@ -96,11 +96,14 @@ static inline unsigned long max(unsigned long a, unsigned long b) { return a > b
 
 static inline int __ffs(int x) { return x ? __builtin_ctz((unsigned)x) + 1 : 0; }
 static inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
+static inline unsigned __brev(unsigned x) { unsigned r = 0; for (int i = 0; i < 32; i++) if (x & (1u << i)) r |= 1u << (31 - i); return r; }
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 static inline int __ffsll(long long x) { return x ? __builtin_ctzll((unsigned long long)x) + 1 : 0; }
 static inline int __clzll(long long x) { return x ? __builtin_clzll((unsigned long long)x) : 64; }
 static inline int __popcll(unsigned long long x) { return __builtin_popcountll(x); }
 static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t s) { return (uint32_t)((((uint64_t)hi << 32) | lo) >> (s & 31)); }
+static inline uint32_t __byte_perm(uint32_t x, uint32_t y, uint32_t s) { const uint64_t v = ((uint64_t)y << 32) | x; uint32_t r = 0; for (int i = 0; i < 4; i++) { const uint32_t sel = (s >> (4 * i)) & 15u; uint32_t b = (uint32_t)(v >> (8 * (sel & 7u))) & 0xFFu; if (sel & 8u) b = (b & 0x80u) ? 0xFFu : 0u; r |= b << (8 * i); } return r; }
+static inline uint32_t __funnelshift_rc(uint32_t lo, uint32_t hi, uint32_t s) { return (uint32_t)((((uint64_t)hi << 32) | lo) >> (s > 32 ? 32 : s)); }
 static inline uint32_t __funnelshift_l(uint32_t lo, uint32_t hi, uint32_t s) { return (uint32_t)(((((uint64_t)hi << 32) | lo) << (s & 31)) >> 32); }
 static inline size_t __cvta_generic_to_shared(const void* p) { return (size_t)p; }
 static inline size_t __cvta_generic_to_global(const void* p) { return (size_t)p; }

@@ -52,7 +52,8 @@ def main():
         hl, stage, algo, sparse = int(parts[0]), int(parts[1]), int(parts[2]), int(parts[3])
         ctypes.c_int.in_dll(lib, "b200lz4_compress_sparse").value = sparse
         ctypes.c_int.in_dll(lib, "b200lz4_compress_hash_log").value = hl
-        ctypes.c_int.in_dll(lib, "b200lz4_compress_stage").value = stage
+        ctypes.c_int.in_dll(lib, "b200lz4_compress_stage").value = 0 if algo == 5 else stage
+        if algo == 5: ctypes.c_int.in_dll(lib, "b200lz4_compress_wide").value = stage      # 10 * sub-rounds + chunk buffers
         ctypes.c_int.in_dll(lib, "b200lz4_compress_algo").value = algo
         t, med = timeit(lambda: B.compress_fast_batch_dev(src, soff, slen, comp, coff, ccap, clen, bs))
         C = int(clen.sum().item())
