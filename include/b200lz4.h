@@ -8,7 +8,7 @@
  *   reference call site (under /root/reference)                       replaced by
  *   src/jni/net_jpountz_lz4_LZ4JNI.c:75   LZ4_compress_default        b200lz4_compress_default
  *   src/jni/net_jpountz_lz4_LZ4JNI.c:122  LZ4_compress_HC             b200lz4_compress_HC
- *   src/jni/net_jpountz_lz4_LZ4JNI.c:169  LZ4_decompress_fast         b200lz4_decompress_fast
+ *   src/jni/net_jpountz_lz4_LZ4JNI.c:169  LZ4_decompress_fast         b200lz4_decompress_fast_bounded
  *   src/jni/net_jpountz_lz4_LZ4JNI.c:216  LZ4_decompress_safe         b200lz4_decompress_safe
  *   src/jni/net_jpountz_lz4_LZ4JNI.c:237  LZ4_compressBound           b200lz4_compressBound
  *   src/jni/net_jpountz_xxhash_XXHashJNI.c:54,78    XXH32             b200xxh32
@@ -41,9 +41,9 @@ extern "C" {
 #endif
 
 #define B200LZ4_VERSION        100          /* 0.1.0 */
-#define B200LZ4_E_NODEVICE     (-1000001)   /* no usable CUDA device / driver            */
-#define B200LZ4_E_CUDA         (-1000002)   /* CUDA runtime error, see b200lz4_last_error */
-#define B200LZ4_E_ARG          (-1000003)   /* invalid argument                           */
+#define B200LZ4_E_NODEVICE     (-2147483647)       /* INT_MIN + 1: no usable CUDA device / driver            */
+#define B200LZ4_E_CUDA         (-2147483646)       /* INT_MIN + 2: CUDA runtime error, see b200lz4_last_error */
+#define B200LZ4_E_ARG          (-2147483645)       /* INT_MIN + 3: invalid argument                           */
 
 /* ---------------------------------------------------------------- library / device */
 int         b200lz4_version(void);
@@ -66,9 +66,10 @@ int b200lz4_compress_HC(const char* src, char* dst, int srcSize, int dstCapacity
 int b200lz4_decompress_safe(const char* src, char* dst, int compressedSize, int dstCapacity);
 /* LZ4_decompress_fast does not know the input size (lz4.c:1788); a device copy needs one.
  * `srcAvail` is the number of readable bytes at src (the Java wrapper knows it:
- * src.length - srcOff).  b200lz4_decompress_fast() assumes compressBound(originalSize). */
+ * src.length - srcOff).  There is deliberately no entry point without it: the host would have to
+ * read compressBound(originalSize) bytes from src, past the end of most callers' buffers.
+ * One-block calls copy back exactly the bytes they produced: dst[result, dstCapacity) is not touched. */
 int b200lz4_decompress_fast_bounded(const char* src, int srcAvail, char* dst, int originalSize);
-int b200lz4_decompress_fast(const char* src, char* dst, int originalSize);
 
 uint32_t b200xxh32(const void* input, size_t len, uint32_t seed);
 uint64_t b200xxh64(const void* input, size_t len, uint64_t seed);

@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # sanitizer / A-B variant build, or the emulator build of tests/simt — via B200LZ4_TEST_SO.
 SO_PATH = os.path.join(_HERE, "libb200lz4.so")
 
-E_NODEVICE, E_CUDA, E_ARG = -1000001, -1000002, -1000003
+E_NODEVICE, E_CUDA, E_ARG = -2147483647, -2147483646, -2147483645      # INT_MIN + 1..3: below every -(offset)-1 a decoder can return
 
 # every symbol include/b200lz4.h declares: (name, restype, argtypes)
 _vp, _i, _sz, _u32, _u64, _i32 = C.c_void_p, C.c_int, C.c_size_t, C.c_uint32, C.c_uint64, C.c_int32
@@ -29,7 +29,6 @@ SYMBOLS = [
     ("b200lz4_compress_HC", _i, [_vp, _vp, _i, _i, _i]),
     ("b200lz4_decompress_safe", _i, [_vp, _vp, _i, _i]),
     ("b200lz4_decompress_fast_bounded", _i, [_vp, _i, _vp, _i]),
-    ("b200lz4_decompress_fast", _i, [_vp, _vp, _i]),
     ("b200xxh32", _u32, [_vp, _sz, _u32]),
     ("b200xxh64", _u64, [_vp, _sz, _u64]),
     ("b200xxh32_create", _vp, [_u32]),

@@ -297,7 +297,15 @@ static int host_batch(Op op, const uint8_t* src_base, const uint64_t* src_off, c
                 end = dst_off[i0 + k] + (uint64_t)(dst_cap[i0 + k] > 0 ? dst_cap[i0 + k] : 0);
             }
         }
-        if (d_span) {
+        if (d_span && n == 1) {
+            // one block per call (the JNI shim's shape): the caller's bytes behind the result stay untouched, like in the
+            // reference (a decoder called with maxDestLen = "rest of my buffer" must not clobber what lies further along),
+            // and no stale staging bytes of another call leave the device.  Costs one more round trip of a few bytes.
+            CK(cudaStreamSynchronize(s.st));
+            const int32_t r = s.h_res()[0];
+            const size_t produced = op == OP_DEC_FAST ? (r >= 0 ? d_span : 0) : (size_t)(r > 0 ? r : 0);
+            if (produced) CK(cudaMemcpyAsync(dst_base + d_lo, s.d_dst + d_phase, produced < d_span ? produced : d_span, cudaMemcpyDeviceToHost, s.st));
+        } else if (d_span) {
             if (contiguous) {
                 CK(cudaMemcpyAsync(dst_base + d_lo, s.d_dst + d_phase, d_span, cudaMemcpyDeviceToHost, s.st));
             } else {
@@ -489,12 +497,12 @@ int b200lz4_compressBound(int n)
 
 int b200lz4_compress_default(const char* src, char* dst, int srcSize, int dstCapacity)
 {
-    if (srcSize < 0 || (unsigned)srcSize > 0x7E000000u) return 0;                    // lz4.c:1324
+    if (srcSize < 0 || (unsigned)srcSize > 0x7E000000u || dstCapacity < 0) return 0;  // lz4.c:1324; no room at all
     return one_block(OP_COMPRESS_FAST, src, srcSize, dst, dstCapacity, srcSize <= 65536 ? 65536 : 0);
 }
 int b200lz4_compress_HC(const char* src, char* dst, int srcSize, int dstCapacity, int level)
 {
-    if (srcSize < 0 || (unsigned)srcSize > 0x7E000000u) return 0;
+    if (srcSize < 0 || (unsigned)srcSize > 0x7E000000u || dstCapacity < 0) return 0;
     return one_block(OP_COMPRESS_HC, src, srcSize, dst, dstCapacity, level);
 }
 int b200lz4_decompress_safe(const char* src, char* dst, int compressedSize, int dstCapacity)
@@ -507,11 +515,6 @@ int b200lz4_decompress_fast_bounded(const char* src, int srcAvail, char* dst, in
 {
     if (!src || originalSize < 0 || srcAvail < 0) return -1;
     return one_block(OP_DEC_FAST, src, srcAvail, dst, originalSize, 0);
-}
-int b200lz4_decompress_fast(const char* src, char* dst, int originalSize)
-{
-    if (originalSize < 0) return -1;
-    return b200lz4_decompress_fast_bounded(src, b200lz4_compressBound(originalSize), dst, originalSize);
 }
 
 uint32_t b200xxh32(const void* input, size_t len, uint32_t seed)

@@ -233,7 +233,7 @@ lz4_compress_fast2_kernel(const uint8_t* __restrict__ src_base, const uint64_t* 
     const int cap = dst_cap[b];
     int ret = 0;
 
-    if (n < 0 || n > 0x7E000000) goto done;                       // lz4.c:1324
+    if (n < 0 || n > 0x7E000000 || cap < 0) goto done;            // lz4.c:1324; no room at all
     if (U16 && n >= 65536 + 11) goto done;                         // lz4.c:973
     if (n == 0) { if (cap >= 1) { if (lane == 0) dst[0] = 0; ret = 1; } goto done; }
     {
@@ -1332,8 +1332,8 @@ extern "C" {
 int b200lz4_compress_hash_log = 13;   // 13 = the reference's table size for <64 KiB blocks (lz4.c:756-762)
 int b200lz4_compress_stage = 0;       // 1 = stage <=64 KiB blocks in shared memory via TMA (v1 parser only)
 int b200lz4_compress_sparse = 0;      // 1 = publish one position in four (pairs with hash_log 12: the 'fast' operating point)
-int b200lz4_compress_algo = 3;        // 3 = decoupled, two-warp pipeline (default); 2 = decoupled, one warp; 1 = coupled warp parser
-int b200lz4_compress_wide = 222;      // algo 5: 100 * warps + 10 * sub-rounds per chunk + chunk buffers
+int b200lz4_compress_algo = 5;        // 3 = decoupled, two-warp pipeline (default); 2 = decoupled, one warp; 1 = coupled warp parser
+int b200lz4_compress_wide = 322;      // algo 5: 100 * warps + 10 * sub-rounds per chunk + chunk buffers
 }
 
 cudaError_t launch_compress_fast(const BatchArgs& a, int max_src_len, cudaStream_t st)

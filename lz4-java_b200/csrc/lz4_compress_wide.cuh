@@ -38,6 +38,7 @@ __device__ __forceinline__ void wide_bar_arrive(int id) { simt::bar_arrive(id, 6
 __device__ __forceinline__ void wide_bar_wait(int id) { simt::bar_sync(id, 64); }
 __device__ __forceinline__ uint32_t ldg_u32(const uint32_t* p) { return *p; }
 __device__ __forceinline__ void ldg_pair(const uint32_t* base, uint32_t idx, uint32_t& lo, uint32_t& hi) { lo = base[idx]; hi = base[idx + 1]; }
+__device__ __forceinline__ uint2 ldg_u64(const uint2* p) { return *p; }
 #else
 // (Immediate barrier ids, so ptxas reserves only the barriers in use and not all 16.)
 #define B200_WBAR_CASE(OP, N) case N: asm volatile(OP " " #N ", 64;" ::: "memory"); break;
@@ -52,6 +53,7 @@ __device__ __forceinline__ void wide_bar_wait(int id)
                   B200_WBAR_CASE("bar.sync", 4) B200_WBAR_CASE("bar.sync", 5) default: asm volatile("bar.sync 6, 64;" ::: "memory"); }
 }
 __device__ __forceinline__ uint32_t ldg_u32(const uint32_t* p) { return __ldg(p); }      // the input is read-only for the kernel
+__device__ __forceinline__ uint2 ldg_u64(const uint2* p) { return __ldg(p); }
 // words idx and idx + 1 of a read-only array: one 32x32+64 multiply-add for the address, two loads off it
 __device__ __forceinline__ void ldg_pair(const uint32_t* base, uint32_t idx, uint32_t& lo, uint32_t& hi)
 {
@@ -109,6 +111,8 @@ lz4_compress_wide_kernel(const uint8_t* __restrict__ src_base, const uint64_t* _
     // aligned-word view of the block: byte a of the view is position a - ph
     const uint32_t ph = uint32_t(reinterpret_cast<uintptr_t>(src)) & 3u;
     const uint32_t* __restrict__ wsrc = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(src) - ph);
+    const uint32_t ph8 = uint32_t(reinterpret_cast<uintptr_t>(src)) & 7u;                 // ... and the same in 8-byte words
+    const uint2* __restrict__ qsrc = reinterpret_cast<const uint2*>(reinterpret_cast<uintptr_t>(src) - ph8);
     const int mflimit = n - 12, matchlimit = n - 5;        // lz4.c:243-244
     const int nchunks = mflimit >= 0 ? (mflimit + int(ph)) / CH + 1 : 0;     // n < 13: all literals (lz4.c:981)
     auto ld4 = [&](int pos) -> uint32_t {                  // the 4 bytes at position pos
@@ -172,9 +176,12 @@ lz4_compress_wide_kernel(const uint8_t* __restrict__ src_base, const uint64_t* _
                     const uint32_t sq = j ? __funnelshift_r(w0[s], w1[s], 8 * j) : w0[s];        // bytes p .. p+3
                     const uint32_t sn = j ? __funnelshift_r(w1[s], w2[s], 8 * j) : w1[s];        // bytes p+4 .. p+7
                     const bool plaus = !EDGE || (p >= 0 && p <= mflimit && cand[s][j] < p);
-                    const uint32_t a = uint32_t(plaus ? cand[s][j] : 0) + ph;                    // (position 0 is always readable)
-                    const uint32_t* w = wsrc + (a >> 2);
-                    const uint32_t c0 = ldg_u32(w), c1 = ldg_u32(w + 1), c2 = ldg_u32(w + 2);
+                    // the candidate's 8 bytes sit in two aligned 8-byte words: two scattered loads instead of three
+                    const uint32_t a = uint32_t(plaus ? cand[s][j] : 0) + ph8;                   // (position 0 is always readable)
+                    const uint2* w = qsrc + (a >> 3);
+                    const uint2 q0 = ldg_u64(w), q1 = ldg_u64(w + 1);
+                    const bool up = (a & 4u) != 0;
+                    const uint32_t c0 = up ? q0.y : q0.x, c1 = up ? q1.x : q0.y, c2 = up ? q1.y : q1.x;
                     const uint32_t x = __funnelshift_r(c0, c1, a << 3) ^ sq;
                     const uint32_t y = __funnelshift_r(c1, c2, a << 3) ^ sn;
                     dd[j] = EDGE ? (uint32_t(p - cand[s][j]) & 0xFFFFu) : uint32_t(p - cand[s][j]);
@@ -367,9 +374,9 @@ lz4_compress_wide_kernel(const uint8_t* __restrict__ src_base, const uint64_t* _
             return m ? 32u * w + uint32_t(__ffs(int(m))) - 1u : uint32_t(CH);
         };
         uint32_t q = search(uint32_t(max(ip - cp0, 0)));
+        uint32_t code = 0, dist = 0;
+        if (q < uint32_t(CH)) { code = fls[q]; dist = ds[q]; }
         while (q < uint32_t(CH)) {
-            const uint32_t code = fls[q];
-            const uint32_t dist = ds[q];
             const uint32_t ms = uint32_t(cp0) + q;
             uint32_t fl = 4u + (code >> 6);
             const uint32_t delta = code & 63u;
@@ -378,9 +385,12 @@ lz4_compress_wide_kernel(const uint8_t* __restrict__ src_base, const uint64_t* _
                 if (delta) fl = 8u + uint32_t(extend(int(ms) + 8, int(dist), matchlimit - (int(ms) + 8)));
                 nq = search(q + fl);
             }
+            // the next sequence's two loads go out before this one is booked: their latency is the chain's critical path
+            uint32_t ncode = 0, ndist = 0;
+            if (nq < uint32_t(CH)) { ncode = fls[nq]; ndist = ds[nq]; }
             if (lane == 0) s_rec[k] = make_uint2(ms | (dist << 16), fl);
             ip = int(ms + fl);
-            q = nq;
+            q = nq; code = ncode; dist = ndist;
             if (++k == 32) flush(false);
         }
         if (c + NB < nchunks) wide_bar_arrive(BAR_FREE + buf);

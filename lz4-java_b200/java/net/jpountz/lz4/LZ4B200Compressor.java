@@ -21,7 +21,7 @@ final class LZ4B200Compressor extends LZ4Compressor {
     checkRange(dest, destOff, maxDestLen);
     final int result = LZ4B200JNI.LZ4_compress_limitedOutput(src, null, srcOff, srcLen, dest, null, destOff, maxDestLen);
     if (result <= 0) {
-      throw new LZ4Exception(result < -1000000 ? "B200 backend error " + result : "maxDestLen is too small");
+      throw new LZ4Exception(result <= Integer.MIN_VALUE + 3 ? "B200 backend error " + result : "maxDestLen is too small");
     }
     return result;
   }
@@ -41,7 +41,7 @@ final class LZ4B200Compressor extends LZ4Compressor {
     final int result = LZ4B200JNI.LZ4_compress_limitedOutput(srcArr, srcArr == null ? src : null, so, srcLen,
         destArr, destArr == null ? dest : null, dof, maxDestLen);
     if (result <= 0) {
-      throw new LZ4Exception(result < -1000000 ? "B200 backend error " + result : "maxDestLen is too small");
+      throw new LZ4Exception(result <= Integer.MIN_VALUE + 3 ? "B200 backend error " + result : "maxDestLen is too small");
     }
     return result;
   }

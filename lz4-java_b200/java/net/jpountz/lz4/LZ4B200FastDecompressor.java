@@ -16,7 +16,7 @@ final class LZ4B200FastDecompressor extends LZ4FastDecompressor {
     checkRange(src, srcOff);
     checkRange(dest, destOff, destLen);
     final int result = LZ4B200JNI.LZ4_decompress_fast(src, null, srcOff, src.length - srcOff, dest, null, destOff, destLen);
-    if (result < -1000000) {
+    if (result <= Integer.MIN_VALUE + 3) {
       throw new LZ4Exception("B200 backend error " + result);   // B200LZ4_E_* (no device / CUDA error): never a CPU fallback
     }
     if (result < 0) {
@@ -40,7 +40,7 @@ final class LZ4B200FastDecompressor extends LZ4FastDecompressor {
     final int avail = src.capacity() - srcOff;
     final int result = LZ4B200JNI.LZ4_decompress_fast(srcArr, srcArr == null ? src : null, so, avail,
         destArr, destArr == null ? dest : null, dof, destLen);
-    if (result < -1000000) {
+    if (result <= Integer.MIN_VALUE + 3) {
       throw new LZ4Exception("B200 backend error " + result);   // B200LZ4_E_* (no device / CUDA error): never a CPU fallback
     }
     if (result < 0) {

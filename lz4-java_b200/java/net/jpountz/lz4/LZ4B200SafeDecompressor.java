@@ -16,7 +16,7 @@ final class LZ4B200SafeDecompressor extends LZ4SafeDecompressor {
     checkRange(src, srcOff, srcLen);
     checkRange(dest, destOff, maxDestLen);
     final int result = LZ4B200JNI.LZ4_decompress_safe(src, null, srcOff, srcLen, dest, null, destOff, maxDestLen);
-    if (result < -1000000) {
+    if (result <= Integer.MIN_VALUE + 3) {
       throw new LZ4Exception("B200 backend error " + result);   // B200LZ4_E_* (no device / CUDA error): never a CPU fallback
     }
     if (result < 0) {
@@ -39,7 +39,7 @@ final class LZ4B200SafeDecompressor extends LZ4SafeDecompressor {
     final int dof = destOff + (destArr != null ? dest.arrayOffset() : 0);
     final int result = LZ4B200JNI.LZ4_decompress_safe(srcArr, srcArr == null ? src : null, so, srcLen,
         destArr, destArr == null ? dest : null, dof, maxDestLen);
-    if (result < -1000000) {
+    if (result <= Integer.MIN_VALUE + 3) {
       throw new LZ4Exception("B200 backend error " + result);   // B200LZ4_E_* (no device / CUDA error): never a CPU fallback
     }
     if (result < 0) {

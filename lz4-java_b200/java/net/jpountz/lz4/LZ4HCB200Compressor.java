@@ -22,7 +22,7 @@ final class LZ4HCB200Compressor extends LZ4Compressor {
     checkRange(src, srcOff, srcLen);
     checkRange(dest, destOff, maxDestLen);
     final int result = LZ4B200JNI.LZ4_compressHC(src, null, srcOff, srcLen, dest, null, destOff, maxDestLen, compressionLevel);
-    if (result < -1000000) {
+    if (result <= Integer.MIN_VALUE + 3) {
       throw new LZ4Exception("B200 backend error " + result);   // B200LZ4_E_*: no device / CUDA error
     }
     if (result <= 0) {
@@ -45,7 +45,7 @@ final class LZ4HCB200Compressor extends LZ4Compressor {
     final int dof = destOff + (destArr != null ? dest.arrayOffset() : 0);
     final int result = LZ4B200JNI.LZ4_compressHC(srcArr, srcArr == null ? src : null, so, srcLen,
         destArr, destArr == null ? dest : null, dof, maxDestLen, compressionLevel);
-    if (result < -1000000) {
+    if (result <= Integer.MIN_VALUE + 3) {
       throw new LZ4Exception("B200 backend error " + result);   // B200LZ4_E_*: no device / CUDA error
     }
     if (result <= 0) {
