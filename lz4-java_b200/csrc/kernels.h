@@ -27,7 +27,6 @@ cudaError_t launch_decompress_safe(const BatchArgs& a, cudaStream_t st);
 cudaError_t launch_decompress_fast(const BatchArgs& a, cudaStream_t st);
 cudaError_t launch_compress_fast(const BatchArgs& a, int max_src_len, cudaStream_t st);
 cudaError_t launch_compress_hc(const BatchArgs& a, int level, cudaStream_t st);
-cudaError_t launch_compress_hc2(const BatchArgs& a, cudaStream_t st);     // experimental second design (lz4hc2_compress.cu)
 cudaError_t launch_xxh32(const uint8_t* base, const uint64_t* off, const int32_t* len, uint32_t seed,
                          uint32_t* out, size_t n, cudaStream_t st);
 // One warp per buffer: for a few long streams (frame content checksums).

@@ -20,13 +20,12 @@
 
 namespace b200 {
 
-// Two builds of each decoder:
-//   * batched (BATCH = true, the default): decode_batch() in front of the sequential code, 56 registers, 32 warps/SM —
-//     up to 32 sequences in flight per warp.  Measured faster at every batch size (64 KiB blocks: 141 vs 75 GiB/s at
-//     2048 blocks, 241 vs 193 at 16384; 4 MiB blocks, one warp each: 47 vs 27);
-//   * sequential (BATCH = false): one sequence at a time, 32 registers, 64 warps/SM.  Kept selectable
-//     (b200lz4_decompress_batch_below = 0) because it is the plain statement of the reference's rules and the
-//     tests run both on the same inputs.
+// Two instantiations of each decoder:
+//   * batched (BATCH = true, what the library launches): decode_batch() in front of the sequential code, 56 registers,
+//     32 warps/SM — up to 32 sequences in flight per warp.  Measured faster at every batch size (64 KiB blocks: 141 vs
+//     75 GiB/s at 2048 blocks, 241 vs 193 at 16384; 4 MiB blocks, one warp each: 47 vs 27);
+//   * sequential (BATCH = false): one sequence at a time — the plain statement of the reference's rules.  Not in the
+//     library; the CPU emulator tests (tests/test_kernel_logic_cpu.py) run both on the same inputs.
 #ifndef B200_DEC_MINB_BATCH
 #define B200_DEC_MINB_BATCH 8
 #endif
@@ -34,9 +33,6 @@ namespace b200 {
 #define B200_DEC_WIN 512
 #endif
 static constexpr int DEC_WIN = B200_DEC_WIN;   // bytes of compressed stream one batch looks at (16 per lane)
-#ifndef B200_DEC_BATCH_BELOW
-#define B200_DEC_BATCH_BELOW 0x7FFFFFFF
-#endif
 
 struct VarLen { uint32_t len; int ip; bool err; };
 
@@ -408,21 +404,12 @@ done:
 #ifndef B200_HOST_SIM          // launchers: CUDA only (tests/simt drives the kernels directly)
 static constexpr int DEC_WARPS = 4;
 
-} // namespace b200
-// Batches with fewer blocks than this use the batched decoders (development knob, like b200lz4_compress_*).
-extern "C" { int b200lz4_decompress_batch_below = B200_DEC_BATCH_BELOW; }
-namespace b200 {
-
 cudaError_t launch_decompress_safe(const BatchArgs& a, cudaStream_t st)
 {
     if (a.n == 0) return cudaSuccess;
     const unsigned grid = (unsigned)((a.n + DEC_WARPS - 1) / DEC_WARPS);
-    if (a.n < (size_t)b200lz4_decompress_batch_below)
-        lz4_decompress_safe_kernel<DEC_WARPS, true><<<grid, DEC_WARPS * 32, 0, st>>>(
-            a.src_base, a.src_off, a.src_len, a.dst_base, a.dst_off, a.dst_cap, a.result, (uint32_t)a.n);
-    else
-        lz4_decompress_safe_kernel<DEC_WARPS, false><<<grid, DEC_WARPS * 32, 0, st>>>(
-            a.src_base, a.src_off, a.src_len, a.dst_base, a.dst_off, a.dst_cap, a.result, (uint32_t)a.n);
+    lz4_decompress_safe_kernel<DEC_WARPS, true><<<grid, DEC_WARPS * 32, 0, st>>>(
+        a.src_base, a.src_off, a.src_len, a.dst_base, a.dst_off, a.dst_cap, a.result, (uint32_t)a.n);
     return cudaGetLastError();
 }
 
@@ -430,12 +417,8 @@ cudaError_t launch_decompress_fast(const BatchArgs& a, cudaStream_t st)
 {
     if (a.n == 0) return cudaSuccess;
     const unsigned grid = (unsigned)((a.n + DEC_WARPS - 1) / DEC_WARPS);
-    if (a.n < (size_t)b200lz4_decompress_batch_below)
-        lz4_decompress_fast_kernel<DEC_WARPS, true><<<grid, DEC_WARPS * 32, 0, st>>>(
-            a.src_base, a.src_off, a.src_len, a.dst_base, a.dst_off, a.dst_cap, a.result, (uint32_t)a.n);
-    else
-        lz4_decompress_fast_kernel<DEC_WARPS, false><<<grid, DEC_WARPS * 32, 0, st>>>(
-            a.src_base, a.src_off, a.src_len, a.dst_base, a.dst_off, a.dst_cap, a.result, (uint32_t)a.n);
+    lz4_decompress_fast_kernel<DEC_WARPS, true><<<grid, DEC_WARPS * 32, 0, st>>>(
+        a.src_base, a.src_off, a.src_len, a.dst_base, a.dst_off, a.dst_cap, a.result, (uint32_t)a.n);
     return cudaGetLastError();
 }
 

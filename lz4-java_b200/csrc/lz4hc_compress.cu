@@ -179,33 +179,27 @@ lz4hc_compress_kernel(const uint8_t* __restrict__ src_base, const uint64_t* __re
     }
 }
 
-#ifndef B200_HOST_SIM          // knobs and launchers: CUDA only
-extern "C" {
-int b200lz4_hc_bucket_log = 11;   // 11 = 2048 buckets, 10 = 1024 buckets
-int b200lz4_hc_algo = 1;          // 1 = this file (default); 2 = lz4hc2_compress.cu (experimental: search everything, DP parse)
-int b200lz4_hc_ways = 32;         // 32 = one position per warp (128 KiB table at 2048 buckets, 1 CTA/SM, best ratio);
-                                  // 16 = one position per half-warp, 8 positions per round (64 KiB, 3 CTAs/SM)
-}
-
-template <int BL, int WAYS>
-static cudaError_t launch_hc(const BatchArgs& a, int level, cudaStream_t st)
+#ifndef B200_HOST_SIM          // launcher: CUDA only
+// 2048 buckets x 32 ways (128 KiB of shared memory, one CTA per SM) is the operating point with the reference's ratio
+// (2048x16 is 2.1x faster at ratio 2.03, 1024x16 3.2x faster at 1.86); other shapes are build-time
+// variants (-DB200_HC_BUCKET_LOG=.. -DB200_HC_WAYS=..), not runtime switches.
+#ifndef B200_HC_BUCKET_LOG
+#define B200_HC_BUCKET_LOG 11
+#endif
+#ifndef B200_HC_WAYS
+#define B200_HC_WAYS 32
+#endif
+cudaError_t launch_compress_hc(const BatchArgs& a, int level, cudaStream_t st)
 {
-    auto k = lz4hc_compress_kernel<BL, WAYS>;
-    const size_t smem = hc_smem<BL, WAYS>() + 80;
+    if (a.n == 0) return cudaSuccess;
+    if (level < 1) level = 9;                                                 // LZ4HC_CLEVEL_DEFAULT, lz4hc.c:840
+    auto k = lz4hc_compress_kernel<B200_HC_BUCKET_LOG, B200_HC_WAYS>;
+    const size_t smem = hc_smem<B200_HC_BUCKET_LOG, B200_HC_WAYS>() + 80;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     k<<<(unsigned)a.n, 128, smem, st>>>(a.src_base, a.src_off, a.src_len, a.dst_base, a.dst_off,
                                         a.dst_cap, a.result, (uint32_t)a.n, level);
     return cudaGetLastError();
-}
-
-cudaError_t launch_compress_hc(const BatchArgs& a, int level, cudaStream_t st)
-{
-    if (a.n == 0) return cudaSuccess;
-    if (level < 1) level = 9;                                                 // LZ4HC_CLEVEL_DEFAULT, lz4hc.c:840
-    if (b200lz4_hc_algo == 2) return launch_compress_hc2(a, st);
-    if (b200lz4_hc_ways == 16) return b200lz4_hc_bucket_log == 10 ? launch_hc<10, 16>(a, level, st) : launch_hc<11, 16>(a, level, st);
-    return b200lz4_hc_bucket_log == 10 ? launch_hc<10, 32>(a, level, st) : launch_hc<11, 32>(a, level, st);
 }
 
 #endif

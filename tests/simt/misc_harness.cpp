@@ -55,20 +55,6 @@ extern "C" uint64_t sim_xxh64_stream(const uint8_t* p, int len, uint64_t seed, c
     return st.digest;
 }
 
-// ---- experimental HC, second design (lz4hc2_compress.cu): K1 search, K2 parse, K3 layout on one block
-#include "../../lz4-java_b200/csrc/lz4hc2_compress.cu"
-
-extern "C" int sim_compress_hc2(const uint8_t* src, int n, uint8_t* dst, int cap, int max_block)
-{
-    uint64_t zero = 0; int32_t sl = n, dc = cap, res = 0x7FFFFFFF, cnt = 0x7FFFFFFF;
-    const uint32_t stride = (uint32_t)((max_block + 3) & ~3), rec_stride = stride / 4 + 16;
-    std::vector<uint32_t> best(stride, 0xDEADBEEFu), cost(stride, 0xDEADBEEFu);
-    std::vector<Hc2Rec> rec(rec_stride);
-    simt::launch(1, HC2_THREADS, [&] { lz4hc2_search_kernel(src, &zero, &sl, 0u, 1u, best.data(), stride); });
-    simt::launch(1, 128, [&] { lz4hc2_parse_kernel(src, &zero, &sl, 0u, 1u, best.data(), cost.data(), stride, rec.data(), rec_stride, &cnt); });
-    simt::launch(1, 128, [&] { lz4hc2_layout_kernel(src, &zero, &sl, dst, &zero, &dc, &res, 0u, 1u, rec.data(), rec_stride, &cnt); });
-    return res;
-}
 
 // ---- compaction (scan + gather)
 #include "../../lz4-java_b200/csrc/compact.cu"

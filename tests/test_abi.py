@@ -107,3 +107,15 @@ def test_java_natives_have_shim_symbols_and_shim_calls_are_in_the_header():
     declared = set(header_functions())
     for call in set(re.findall(r"\b(b200(?:lz4|xxh(?:32|64))_?\w*)\s*\(", shim)):
         assert call in declared, call
+
+
+def test_library_exports_nothing_but_the_header():
+    """nm -D: the dynamic symbol table holds the C ABI of include/b200lz4.h and nothing else — no tuning knobs (round 1 had
+    process-global ints a test could flip under every other thread's feet), no kernel stubs, no internal launch layer"""
+    import re, subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run(["nm", "-D", "--defined-only", os.path.join(root, "lz4-java_b200", "libb200lz4.so")],
+                         capture_output=True, text=True, check=True).stdout
+    exported = {l.split()[-1] for l in out.splitlines() if l.strip()}
+    declared = set(re.findall(r"\b(b200[A-Za-z0-9_]*)\s*\(", open(os.path.join(root, "include", "b200lz4.h")).read()))
+    assert exported == declared, (sorted(exported - declared), sorted(declared - exported))

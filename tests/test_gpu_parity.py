@@ -21,16 +21,11 @@ def _slots(lens, extra=0, align=16):
     return np.array(offs, dtype=np.uint64), np.array(caps, dtype=np.int32), pos + 64
 
 
-@pytest.fixture(params=["batched", "sequential"])
-def decoder(request, b200):
-    """Both builds of the decoders on the same inputs: decode_batch() in front (few / large blocks) and the
-    one-sequence-at-a-time kernels (the library picks by batch size; the knob forces one)."""
-    import ctypes
-    knob = ctypes.c_int.in_dll(b200._native.lib(), "b200lz4_decompress_batch_below")
-    old = knob.value
-    knob.value = (1 << 30) if request.param == "batched" else 0
-    yield request.param
-    knob.value = old
+@pytest.fixture
+def decoder():
+    """The library launches the batched decoders (decode_batch() in front of the sequential code); the sequential-only
+    instantiation is exercised on the CPU emulator (tests/test_kernel_logic_cpu.py)."""
+    return "batched"
 
 
 def test_decompress_safe_exact(b200, checker, decoder):
@@ -211,28 +206,30 @@ def test_decompress_long_sequence_then_short_ones_near_the_end(b200, checker, de
         assert (dst[int(doff[k]) + len(d):int(doff[k]) + len(d) + 16] == 0x55).all(), (decoder, "fast", k)
 
 
-def _knob(b200, name, value):
-    import ctypes
-    ctypes.c_int.in_dll(b200._native.lib(), name).value = value
-
-
-@pytest.mark.parametrize("table", ["u16", "u16_hl12", "u16_sparse", "u16_hl12_sparse", "u32", "v4_u16", "v4_u16_hl12_sparse", "v4_u32", "v2_u16", "v2_u32", "v1_u16", "v1_u16_hl12", "v1_u16_tma_staged", "v1_u32"])
+@pytest.mark.parametrize("table", ["u16", "u32"])
 def test_compress_roundtrip_through_oracle(b200, checker, table):
+    """u16: blocks <= 64 KiB (three-warp kernel, 8192 x u16 table, lz4.c:1353); u32: any size (one warp, 4096 x u32, lz4.c:1356)"""
     items = corpus.blocks(checker) + corpus.calgary_blocks()
-    if not table.endswith("u32"):           # 16-bit position table: caller promises blocks <= 64 KiB
+    if table == "u16":                      # 16-bit position table: caller promises blocks <= 64 KiB
         items = [(nm, d) for nm, d in items if len(d) <= 65536]
-    max_src_len = 0 if table.endswith("u32") else 65536
-    _knob(b200, "b200lz4_compress_algo", 1 if table.startswith("v1") else 2 if table.startswith("v2") else 4 if table.startswith("v4") else 3)   # 3 = two-warp pipeline (default)
-    _knob(b200, "b200lz4_compress_hash_log", 12 if "hl12" in table else 13)
-    _knob(b200, "b200lz4_compress_stage", 1 if "staged" in table else 0)
-    _knob(b200, "b200lz4_compress_sparse", 1 if "sparse" in table else 0)
-    try:
-        _compress_roundtrip(b200, checker, items, max_src_len, slack=1.25 if "hl12" in table else 1.10)
-    finally:
-        _knob(b200, "b200lz4_compress_algo", 3)
-        _knob(b200, "b200lz4_compress_hash_log", 13)
-        _knob(b200, "b200lz4_compress_stage", 0)
-        _knob(b200, "b200lz4_compress_sparse", 0)
+    _compress_roundtrip(b200, checker, items, 65536 if table == "u16" else 0, slack=1.10)
+
+
+def test_compress_streams_are_the_pinned_ones(b200, checker):
+    """tests/golden/fast_streams.json: the bytes the kernel source emits on the CPU emulator for the seeded corpus (and
+    emitted on the GPU in round 1) are the bytes the GPU emits now — sizes and SHA-256 of every stream"""
+    import hashlib, json, os
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fast_streams.json")))["streams"]
+    items = [(nm, d) for nm, d in corpus.blocks(checker) if nm in gold]
+    assert len(items) == len(gold)
+    src, soff, slen = corpus.pack([d for _, d in items], align=4)
+    bounds = [b200.max_compressed_length(len(d)) for _, d in items]
+    doff, dcap, total = _slots(bounds)
+    dst = np.zeros(total + 64, dtype=np.uint8)
+    res = b200.batch.compress_fast_batch_host(src, soff, slen, dst, doff, dcap, max_src_len=65536)
+    for k, (nm, d) in enumerate(items):
+        c = dst[int(doff[k]):int(doff[k]) + int(res[k])].tobytes()
+        assert (int(res[k]), hashlib.sha256(c).hexdigest()) == (gold[nm]["c"], gold[nm]["sha256"]), nm
 
 
 def _compress_roundtrip(b200, checker, items, max_src_len, slack):
@@ -523,32 +520,6 @@ def test_hc_compress_roundtrip_and_ratio(b200, checker):
     for lvl in (-5, 1, 9, 17, 99):
         c = F.highCompressor(lvl).compress(d)
         assert checker.decompress_safe(c, len(d))[1] == d
-
-
-@pytest.mark.skipif(not __import__("os").environ.get("B200_EXPERIMENTAL"),
-                    reason="lz4hc2_compress.cu has only run on the CPU emulator so far (tests/test_kernel_logic_cpu.py); "
-                           "set B200_EXPERIMENTAL=1 to run it on the GPU")
-def test_hc_second_design_on_gpu(b200, checker):
-    """b200lz4_hc_algo = 2 (search every position, DP parse): same contract as the default HC kernel, and a ratio at least
-    as good on the same inputs"""
-    items = [(nm, d) for nm, d in corpus.blocks(checker) if len(d) in (0, 1, 12, 13, 64, 1000, 4096, 65536) or nm.startswith("period")]
-    items += [(f"rdg256k_{mp}", checker.datagen(262144, mp, 0.0, 4).tobytes()) for mp in (0.2, 0.5, 0.8)]
-    items += corpus.calgary_blocks(2)
-    src, soff, slen = corpus.pack([d for _, d in items])
-    bounds = [b200.max_compressed_length(len(d)) for _, d in items]
-    doff, dcap, total = _slots(bounds)
-    first = b200.batch.compress_hc_batch_host(src, soff, slen, np.zeros(total, dtype=np.uint8), doff, dcap, level=9)
-    _knob(b200, "b200lz4_hc_algo", 2)
-    try:
-        dst = np.zeros(total, dtype=np.uint8)
-        res = b200.batch.compress_hc_batch_host(src, soff, slen, dst, doff, dcap, level=9)
-    finally:
-        _knob(b200, "b200lz4_hc_algo", 1)
-    for k, (name, d) in enumerate(items):
-        assert 0 < res[k] <= bounds[k], (name, int(res[k]))
-        r, out = checker.decompress_safe(dst[int(doff[k]):int(doff[k]) + int(res[k])].tobytes(), len(d))
-        assert r == len(d) and out == d, name
-    assert int(res.sum()) <= int(first.sum()) * 1.005, (int(res.sum()), int(first.sum()))
 
 
 def test_frame_batch_decoder(b200, port):
@@ -985,3 +956,141 @@ def test_reference_test_fixtures_on_gpu(b200, port):
         assert port.frame_decompress(fr, n + 8) == (n, data), n
         if n <= (1 << 20):
             assert b200.decompress_lz4block(b200.compress_lz4block(data, 1 << 16), n + 8) == data, n
+
+
+# ---------------------------------------------------------------------------------------------- round-2 additions
+def test_golden_skippable_frame(b200):
+    """src/lz4/tests/goldenSamples/skip.bin, the reference's only golden file: a skippable frame decodes to nothing, alone
+    and in front of / behind a real frame (LZ4FrameInputStream.java:154-173)"""
+    import json, os
+    blob = bytes.fromhex(json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "skip_bin.json")))["hex"])
+    assert len(blob) == 38
+    assert b200.decompress_frames(blob, 16) == b""
+    data = bytes(range(256)) * 300
+    f = b200.compress_frame(data, 4, True, False, False)
+    assert b200.decompress_frames(blob + f + blob, len(data)) == data
+
+
+@pytest.mark.parametrize("mp", [0.2, 0.5, 0.8])
+def test_dev_pointer_entry_points_sweep(b200, checker, mp):
+    """Every *_batch_dev entry point (what bench.py times) with device tensors on a NON-default stream, the sweep that found
+    round 1's decoder bug: 16384 x 64 KiB blocks of RDG_genBuffer, bound-sized compressed slots that still hold the streams
+    of ANOTHER corpus behind each stream's end, safe and fast decoders, against oracle/_ref: the reference decodes the
+    GPU's streams, the GPU decodes the reference's streams, return codes for every block."""
+    import torch
+    from oracle import oracle as O
+    n, bs = 16384, 65536
+    dev = torch.device("cuda", 0)
+    bound = b200.max_compressed_length(bs); stride = (bound + 15) // 16 * 16
+    B = b200.batch
+    threads = min(32, os.cpu_count() or 1)
+
+    def corpus_of(p, seed):
+        base = checker.datagen(2048 * bs, p, 0.0, seed)
+        return np.tile(base, n // 2048)
+
+    other = corpus_of(0.5 if mp != 0.5 else 0.8, 11)          # what the slots held before
+    data = corpus_of(mp, 7)
+    for k in range(n):                                          # make the tiled blocks distinct
+        data[k * bs] ^= k & 0xFF; data[k * bs + 1] ^= (k >> 8) & 0xFF
+    soff = torch.arange(n, device=dev, dtype=torch.int64) * bs
+    slen = torch.full((n,), bs, device=dev, dtype=torch.int32)
+    coff = torch.arange(n, device=dev, dtype=torch.int64) * stride
+    ccap = torch.full((n,), bound, device=dev, dtype=torch.int32)
+    st = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(st):
+        d_src = torch.from_numpy(data).to(dev, non_blocking=False)
+        comp = torch.zeros(n * stride, dtype=torch.uint8, device=dev)
+        clen = torch.zeros(n, dtype=torch.int32, device=dev)
+        res = torch.zeros(n, dtype=torch.int32, device=dev)
+        out = torch.zeros(n * bs, dtype=torch.uint8, device=dev)
+        d_other = torch.from_numpy(other).to(dev)
+        B.compress_fast_batch_dev(d_other, soff, slen, comp, coff, ccap, clen, bs)      # stale streams in every slot
+        B.compress_fast_batch_dev(d_src, soff, slen, comp, coff, ccap, clen, bs)
+        B.decompress_safe_batch_dev(comp, coff, clen, out, soff, slen, res)
+        st.synchronize()
+        assert bool((clen > 0).all()) and bool((res == bs).all()) and bool(torch.equal(out, d_src)), "safe"
+        out.zero_()
+        B.decompress_fast_batch_dev(comp, coff, ccap, out, soff, slen, res)            # readable bytes = the whole slot
+        st.synchronize()
+        assert bool((res == clen).all()) and bool(torch.equal(out, d_src)), "fast"
+        h_comp, h_clen = comp.cpu().numpy(), clen.cpu().numpy()
+    # the reference decodes every GPU stream
+    np_off = np.arange(n, dtype=np.uint64)
+    back = np.zeros(n * bs, dtype=np.uint8)
+    _, _, r = O.cpu_bench(checker, "dec_safe", h_comp, np_off * np.uint64(stride), h_clen.astype(np.int32), back,
+                          np_off * np.uint64(bs), np.full(n, bs, dtype=np.int32), threads, 1)
+    assert (r == bs).all() and (back == data).all(), "reference rejects a GPU stream"
+    # the GPU decodes every reference stream (slots keep the GPU's longer/shorter streams behind them)
+    ref_comp = h_comp.copy()
+    _, _, rc = O.cpu_bench(checker, "compress", data, np_off * np.uint64(bs), np.full(n, bs, dtype=np.int32), ref_comp,
+                           np_off * np.uint64(stride), np.full(n, bound, dtype=np.int32), threads, 1)
+    assert (rc > 0).all()
+    with torch.cuda.stream(st):
+        comp.copy_(torch.from_numpy(ref_comp)); rlen = torch.from_numpy(rc.astype(np.int32)).to(dev)
+        out.zero_(); B.decompress_safe_batch_dev(comp, coff, rlen, out, soff, slen, res); st.synchronize()
+        assert bool((res == bs).all()) and bool(torch.equal(out, d_src)), "safe / reference streams"
+        out.zero_(); B.decompress_fast_batch_dev(comp, coff, ccap, out, soff, slen, res); st.synchronize()
+        assert bool((res == rlen).all()) and bool(torch.equal(out, d_src)), "fast / reference streams"
+        # hashes through the device entry points, same stream
+        h64 = torch.zeros(n, dtype=torch.int64, device=dev); h32 = torch.zeros(n, dtype=torch.int32, device=dev)
+        B.xxh64_batch_dev(d_src, soff, slen, h64, 0); B.xxh32_batch_dev(d_src, soff, slen, h32, 0x9747B28C); st.synchronize()
+        for k in (0, 1, n // 2, n - 1):
+            blk = data[k * bs:(k + 1) * bs]
+            assert (int(h64[k]) & (2 ** 64 - 1)) == checker.xxh64(blk, 0) and (int(h32[k]) & 0xFFFFFFFF) == checker.xxh32(blk, 0x9747B28C)
+        # HC through its device entry point on a slice
+        m = 64
+        B.compress_hc_batch_dev(d_src, soff[:m], slen[:m], comp, coff[:m], ccap[:m], clen[:m], 9)
+        out.zero_(); B.decompress_safe_batch_dev(comp, coff[:m], clen[:m], out, soff[:m], slen[:m], res[:m]); st.synchronize()
+        assert bool((res[:m] == bs).all()) and bool(torch.equal(out[:m * bs], d_src[:m * bs])), "hc"
+
+
+def test_negative_and_tiny_capacities(b200, checker):
+    """dstCapacity < 0 is "no room" (0, nothing written), not a wrapped unsigned comparison (round-1 advisor finding);
+    the reference returns 0 for every capacity below what it needs (lz4.c:1085-1088)"""
+    d = checker.datagen(20000, 0.5, 0.0, 3).tobytes()
+    src, soff, slen = corpus.pack([d, d, d, d])
+    need = len(checker.compress(d))
+    caps = np.array([-1, -(1 << 31), 0, need - 1], dtype=np.int32)
+    doff = np.arange(4, dtype=np.uint64) * np.uint64(32768)
+    for max_src_len in (65536, 0):
+        dst = np.full(4 * 32768, 0x55, dtype=np.uint8)
+        res = b200.batch.compress_fast_batch_host(src, soff, slen, dst, doff, caps, max_src_len=max_src_len)
+        assert (res == 0).all(), res
+        assert (dst[:3 * 32768] == 0x55).all()
+    assert b200._native.lib().b200lz4_compress_default(src.ctypes.data, dst.ctypes.data, len(d), -1) == 0
+    assert b200._native.lib().b200lz4_compress_HC(src.ctypes.data, dst.ctypes.data, len(d), -5, 9) == 0
+
+
+def test_one_block_calls_leave_the_rest_of_dst_alone(b200, checker):
+    """a decoder called with maxDestLen = "the rest of my buffer" must not clobber what lies further along (the reference
+    only scribbles a few bytes past what it writes); compress likewise copies back exactly its output"""
+    f = b200.LZ4Factory.b200Instance()
+    a = checker.datagen(5000, 0.5, 0.0, 1).tobytes(); b = checker.datagen(7000, 0.5, 0.0, 2).tobytes()
+    ca, cb = checker.compress(a), checker.compress(b)
+    dest = bytearray(b"\xAA" * 20000)
+    assert f.safeDecompressor().decompress(cb, 0, len(cb), dest, 5000, 15000) == len(b)      # block 2 first, further along
+    assert f.safeDecompressor().decompress(ca, 0, len(ca), dest, 0, 20000) == len(a)         # block 1 with the whole buffer as room
+    assert bytes(dest[:5000]) == a and bytes(dest[5000:12000]) == b and bytes(dest[12000:]) == b"\xAA" * 8000
+    out = bytearray(b"\x33" * 30000)
+    n = f.fastCompressor().compress(a, 0, len(a), out, 100, 20000)
+    assert checker.decompress_safe(bytes(out[100:100 + n]), len(a)) == (len(a), a)
+    assert bytes(out[:100]) == b"\x33" * 100 and bytes(out[100 + n:]) == b"\x33" * (30000 - 100 - n)
+
+
+def test_error_offsets_beyond_a_million_are_decoder_errors(b200, checker):
+    """-(offset)-1 of a corrupt 4 MiB frame block can be below -1000000: it must surface as "Error decoding offset N"
+    (LZ4JNISafeDecompressor.java:40-42), not as a backend failure (the backend codes are INT_MIN + 1..3)"""
+    d = checker.datagen(4 << 20, 0.2, 0.0, 5).tobytes()
+    c = bytearray(checker.compress(d))
+    assert len(c) > 3_000_000
+    c = c[:len(c) - 7]                                          # cut inside the last literals: the error sits at the very end
+    want, _ = checker.decompress_safe(bytes(c), len(d))
+    assert want < -1_000_000
+    src = np.frombuffer(bytes(c), dtype=np.uint8)
+    dst = np.zeros(len(d), dtype=np.uint8)
+    r = b200._native.lib().b200lz4_decompress_safe(src.ctypes.data, dst.ctypes.data, len(c), len(d))
+    assert r == want
+    with pytest.raises(b200.LZ4Exception) as e:
+        b200.LZ4Factory.b200Instance().safeDecompressor().decompress(bytes(c), 0, len(c), bytearray(len(d)), 0, len(d))
+    assert "offset" in str(e.value)

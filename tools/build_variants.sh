@@ -12,6 +12,6 @@ for spec in "$@"; do
   for f in lz4_compress lz4_decompress; do
     nvcc -std=c++17 -O3 -lineinfo $ARCH -Xcompiler -fPIC --expt-relaxed-constexpr $flags -c $f.cu -o /tmp/${f}_$name.o
   done
-  nvcc $ARCH -shared -o ../../variants/libb200lz4_$name.so capi.o /tmp/lz4_decompress_$name.o /tmp/lz4_compress_$name.o lz4hc_compress.o lz4hc2_compress.o xxhash.o compact.o frame.o containers.o
+  nvcc $ARCH -shared -o ../../variants/libb200lz4_$name.so capi.o /tmp/lz4_decompress_$name.o /tmp/lz4_compress_$name.o lz4hc_compress.o xxhash.o compact.o frame.o containers.o -Xlinker --version-script=exports.map
   echo "built variants/libb200lz4_$name.so ($flags)"
 done

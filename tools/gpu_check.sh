@@ -5,4 +5,4 @@ ulimit -c 0
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q -W ignore::DeprecationWarning > gpurun_out/gpu_tests.log 2>&1
 tail -3 gpurun_out/gpu_tests.log | cut -c1-300
-VARIANTS=${VARIANTS:-13:0:3:0,12:0:3:0,13:0:3:1} timeout 600 python tools/probe.py 2>&1 | tail -12
+timeout 600 python tools/probe.py 2>&1 | tail -12

@@ -42,24 +42,11 @@ def main():
     res = torch.zeros(nblk, device=dev, dtype=torch.int32)
     B = L.batch
     N = nblk * bs
-    import ctypes
-    lib = L._native.lib()
-    if os.environ.get("DEC_BELOW"):
-        ctypes.c_int.in_dll(lib, "b200lz4_decompress_batch_below").value = int(os.environ["DEC_BELOW"])
-    variants = os.environ.get("VARIANTS", "13:0:3,12:0:3,13:0:2,12:0:2,13:0:1")
-    for v in variants.split(","):
-        parts = v.split(":") + ["3", "0"]
-        hl, stage, algo, sparse = int(parts[0]), int(parts[1]), int(parts[2]), int(parts[3])
-        ctypes.c_int.in_dll(lib, "b200lz4_compress_sparse").value = sparse
-        ctypes.c_int.in_dll(lib, "b200lz4_compress_hash_log").value = hl
-        ctypes.c_int.in_dll(lib, "b200lz4_compress_stage").value = 0 if algo == 5 else stage
-        if algo == 5: ctypes.c_int.in_dll(lib, "b200lz4_compress_wide").value = stage      # 10 * sub-rounds + chunk buffers
-        ctypes.c_int.in_dll(lib, "b200lz4_compress_algo").value = algo
-        t, med = timeit(lambda: B.compress_fast_batch_dev(src, soff, slen, comp, coff, ccap, clen, bs))
-        C = int(clen.sum().item())
-        out.zero_(); B.decompress_safe_batch_dev(comp, coff, clen, out, soff, slen, res)
-        rt = bool((res == bs).all().item()) and bool(torch.equal(out, src))
-        print(f"compress hl={hl} stage={stage} algo={algo} sparse={sparse}: {N/t/2**30:.1f} GiB/s best ({N/med/2**30:.1f} med)  ratio {N/C:.3f}  hbm {(N+C)/t/1e9:.0f} GB/s  roundtrip={rt}", flush=True)
+    t, med = timeit(lambda: B.compress_fast_batch_dev(src, soff, slen, comp, coff, ccap, clen, bs))
+    C = int(clen.sum().item())
+    out.zero_(); B.decompress_safe_batch_dev(comp, coff, clen, out, soff, slen, res)
+    rt = bool((res == bs).all().item()) and bool(torch.equal(out, src))
+    print(f"compress: {N/t/2**30:.1f} GiB/s best ({N/med/2**30:.1f} med)  ratio {N/C:.3f}  hbm {(N+C)/t/1e9:.0f} GB/s  roundtrip={rt}", flush=True)
     if os.environ.get("COMPRESS_ONLY"): return
     t, med = timeit(lambda: B.decompress_safe_batch_dev(comp, coff, clen, out, soff, slen, res))
     ok = bool((res == bs).all().item()) and bool(torch.equal(out, src))
@@ -90,7 +77,6 @@ if __name__ == "__main__" and not os.environ.get("HC"):
 
 def hc_probe():
     """config 4 shape: 256 KiB blocks, HC level 9 — ratio vs the reference's LZ4_compress_HC(9) and GiB/s"""
-    import ctypes
     nblk = int(os.environ.get("HC_NBLK", 2048)); bs = 262144
     chk = O.best_available()
     base_n = min(nblk, 256)
@@ -104,7 +90,6 @@ def hc_probe():
     ccap = torch.full((nblk,), bound, device=dev, dtype=torch.int32)
     comp = torch.zeros(nblk * stride, device=dev, dtype=torch.uint8)
     clen = torch.zeros(nblk, device=dev, dtype=torch.int32)
-    ctypes.c_int.in_dll(L._native.lib(), "b200lz4_hc_bucket_log").value = int(os.environ.get("HC_BL", 11))
     t, med = timeit(lambda: L.batch.compress_hc_batch_dev(src, soff, slen, comp, coff, ccap, clen, 9), iters=2, warm=1)
     N = nblk * bs; C = int(clen.sum().item())
     ref_c = sum(len(chk.compress_hc(host[i * bs:(i + 1) * bs], 9)) for i in range(4)) if hasattr(chk, "compress_hc") else 0
