@@ -220,6 +220,338 @@ def run_reference(args):
     return 0
 
 
+# ------------------------------------------------------------------------------------------ NUMA
+def numa_bind(local):
+    """Pin this process (its pinned allocations follow by first touch) to the CPUs of the NUMA node GPU `local` hangs off.
+    Round 1's 8-GPU end-to-end run scaled 0.355 with ranks floating over both sockets.  Best effort; returns what it did."""
+    try:
+        import torch
+        bus = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(local)).busId
+            bus = bus.decode() if isinstance(bus, bytes) else bus
+        except Exception:
+            bus = subprocess.run(["nvidia-smi", f"--id={local}", "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                                 capture_output=True, text=True, timeout=20).stdout.strip()
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:                       # 00000000:1b:00.0 -> 0000:1b:00.0
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return {"gpu_pci": bus, "node": None, "note": "no NUMA node reported"}
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus |= set(range(int(a), int(b or a) + 1))
+        mine = os.sched_getaffinity(0) & cpus
+        if mine:
+            os.sched_setaffinity(0, mine)
+        return {"gpu_pci": bus, "node": node, "cpus": len(mine)}
+    except Exception as e:          # noqa: BLE001
+        return {"node": None, "note": f"not bound: {e}"}
+
+
+def timed(fn, iters, warm, torch):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) / 1e3)
+    return min(ts), sorted(ts)[len(ts) // 2]
+
+
+def reduce_max(torch, dist, dev, world, *vals):
+    t = torch.tensor(list(vals), device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(x) for x in t.tolist()]
+
+
+# ------------------------------------------------------------------------------------------ secondary configs (BASELINE configs[2..4])
+def run_config5(args, L, chk, torch, dist, dev, rank, world, local, peak):
+    """configs[4]: XXH64 over 100 M x 4 KiB buffers on 8 B200 = 12.5 M buffers (51.2 GB) per GPU, weak scaling; seeds 0 and
+    0x9747b28c (lz4-java's default, LZ4BlockOutputStream.java:56); xxhash.c:855-879, stripe loop :832-837"""
+    n = args.xxh_buffers
+    data = torch.empty(n * 4096, dtype=torch.uint8, device=dev)
+    g = torch.Generator(device=dev); g.manual_seed(1234 + rank)
+    base = torch.randint(0, 256, (1 << 28,), dtype=torch.uint8, device=dev, generator=g)
+    for i in range(0, n * 4096, 1 << 28):
+        data[i:i + (1 << 28)] = base[: min(1 << 28, n * 4096 - i)]
+    idx = torch.arange(n, device=dev, dtype=torch.int64) + rank * n
+    v = data.view(n, 4096)
+    for k in range(8):
+        v[:, k] ^= ((idx >> (8 * k)) & 0xFF).to(torch.uint8)     # every buffer distinct
+    del base
+    off = torch.arange(n, device=dev, dtype=torch.int64) * 4096
+    ln = torch.full((n,), 4096, device=dev, dtype=torch.int32)
+    o64 = torch.zeros(n, device=dev, dtype=torch.int64)
+    o32 = torch.zeros(n, device=dev, dtype=torch.int32)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    if world > 1:
+        dist.barrier()
+    t64, _ = timed(lambda: L.batch.xxh64_batch_dev(data, off, ln, o64, 0), 5, 3, torch)
+    t64b, _ = timed(lambda: L.batch.xxh64_batch_dev(data, off, ln, o64, 0x9747B28C), 5, 1, torch)
+    t32, _ = timed(lambda: L.batch.xxh32_batch_dev(data, off, ln, o32, 0x9747B28C), 5, 1, torch)
+    clocks = sampler.stop() if rank == 0 else None
+    import random
+    rng = random.Random(5 + rank)
+    picks = [0, 1, n - 1] + [rng.randrange(n) for _ in range(253)]
+    L.batch.xxh64_batch_dev(data, off, ln, o64, 0)
+    for k in picks:                                                  # sampled _ref check, outside the timed region
+        b = data[k * 4096:(k + 1) * 4096].cpu().numpy()
+        if (int(o64[k].item()) & (2 ** 64 - 1)) != chk.xxh64(b, 0) or (int(o32[k].item()) & 0xFFFFFFFF) != chk.xxh32(b, 0x9747B28C):
+            raise SystemExit("bench: config5 hash mismatch against the CPU checker")
+    t64, t64b, t32 = reduce_max(torch, dist, dev, world, t64, t64b, t32)
+    del data, v
+    torch.cuda.empty_cache()
+    by = n * (4096 + 8)
+    return {"metric": "xxh64_4KiB_buffers", "value": by * world / t64 / 1e9, "unit": "GB/s",
+            "workload": f"{n} x 4 KiB buffers per GPU (configs[4]: 100 M over 8 GPUs = 12.5 M per GPU), seed 0",
+            "buffers_per_gpu": n, "seed_0x9747b28c_GBps": by * world / t64b / 1e9, "xxh32_GBps": n * 4100 * world / t32 / 1e9,
+            "roofline": {"bound": "hbm", "kernel": "xxh_batch_kernel<64>", "achieved": by / t64 / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": by / t64 / 1e9 / peak, "algorithmic_bytes_per_launch": by, "note": "len + 8 per buffer; a read-only stream can exceed a copy-measured peak"},
+            "clocks": clocks, "verified": "256 sampled buffers per GPU bit-exact vs the CPU checker (XXH64 seed 0, XXH32 seed 0x9747b28c)"}
+
+
+def run_config3(args, L, chk, torch, dist, dev, rank, world, local, peak):
+    """configs[2]: LZ4FrameInputStream decode (LZ4FrameInputStream.java:132-321; content checksum :264-273) of 16 GiB of
+    4 MiB independent-block frames + XXH32 content checksum over 8 B200, sharded by FRAME = 32 frames of 64 MiB per GPU"""
+    import numpy as np
+    lib = L._native.lib()
+    nframes, fsize = args.frames, 64 << 20
+    ndistinct = min(4, nframes)                                      # 4 x 40 MiB of compressed frames cycle: larger than L2
+    originals = [chk.datagen(fsize, 0.5, 0.0, 31 + 7 * rank + j) for j in range(ndistinct)]
+    frames = [np.frombuffer(chk.frame_compress(o, 7, 1), dtype=np.uint8) for o in originals]      # bsID 7 = 4 MiB, content checksum
+    host = np.concatenate([frames[i % ndistinct] for i in range(nframes)])
+    slot = ctypes.c_uint64(); err = ctypes.c_int()
+    index = lib.b200lz4f_index_create(host.ctypes.data, len(host), ctypes.byref(slot), ctypes.byref(err))
+    if not index:
+        raise SystemExit(f"bench: config3 index error {err.value}")
+    d_src = torch.from_numpy(host).to(dev)
+    d_slots = torch.empty(slot.value + 16, dtype=torch.uint8, device=dev)
+    foff = np.zeros(nframes, dtype=np.uint64); flen = np.zeros(nframes, dtype=np.uint64)
+    st = torch.cuda.current_stream().cuda_stream
+    total = nframes * fsize
+
+    def run():
+        r = lib.b200lz4f_decode_dev(index, d_src.data_ptr(), d_slots.data_ptr(), foff.ctypes.data, flen.ctypes.data, None, st)
+        if r != total:
+            raise SystemExit(f"bench: config3 decode returned {r}")
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    if world > 1:
+        dist.barrier()
+    t, _ = timed(run, 5, 2, torch)
+    clocks = sampler.stop() if rank == 0 else None
+    for i in (0, 1, nframes - 1):                                    # decoded bytes against the original
+        got = d_slots[int(foff[i]):int(foff[i]) + fsize]
+        if not torch.equal(got.cpu(), torch.from_numpy(originals[i % ndistinct])):
+            raise SystemExit("bench: config3 decoded bytes differ from the original")
+    # end to end from (pinned) host memory through the one-call API
+    pin_in = torch.from_numpy(host).pin_memory(); pin_out = torch.empty(total, dtype=torch.uint8).pin_memory()
+    te = 1e30
+    for _ in range(3):
+        t1 = time.perf_counter()
+        r = lib.b200lz4f_decompress_host(pin_in.data_ptr(), len(host), pin_out.data_ptr(), total)
+        te = min(te, time.perf_counter() - t1)
+    if r != total or not torch.equal(pin_out[:fsize], torch.from_numpy(originals[0])):
+        raise SystemExit("bench: config3 host path mismatch")
+    blocks = int(lib.b200lz4f_index_blocks(index))
+    lib.b200lz4f_index_free(index)
+    t, te = reduce_max(torch, dist, dev, world, t, te)
+    csize = len(host)
+    del d_src, d_slots, pin_in, pin_out
+    torch.cuda.empty_cache()
+    algo = csize + 2 * total                                         # C read, N written, N read again by the content hash
+    return {"metric": "lz4_frame_decode_4MiB_blocks_content_xxh32", "value": total * world / t / GIB, "unit": "GiB/s",
+            "workload": f"{nframes} frames x 64 MiB per GPU (configs[2]: 256 frames = 16 GiB over 8 GPUs, sharded by frame), "
+                        "4 MiB independent blocks, content checksum, frames written by the reference's LZ4F_compressFrame, RDG P=0.50",
+            "frames_per_gpu": nframes, "blocks_per_gpu": blocks, "e2e_host_GiBps": total * world / te / GIB,
+            "roofline": {"bound": "hbm", "kernel": "lz4_decompress_safe_kernel + xxh32_long_kernel", "achieved": algo / t / 1e9, "peak": peak,
+                         "unit": "GB/s", "frac": algo / t / 1e9 / peak, "algorithmic_bytes_per_launch": algo,
+                         "note": "C + 2N: the content hash is a second pass over the decoded bytes; one warp per 4 MiB block and one per frame "
+                                 "(XXH32 is four serial chains per stream) bound this far below HBM"},
+            "clocks": clocks, "verified": "3 frames per GPU compared with the original bytes; header + content checksums verified on the device"}
+
+
+def run_config4(args, L, chk, torch, dist, dev, rank, world, local, peak):
+    """configs[3]: LZ4_compress_HC level 9 (lz4hc.c:958-973) over 256 K x 256 KiB blocks = 64 GiB on one B200, ratio next to
+    the reference's on the same bytes.  The pass is sized to about a minute: the stated 262 144 blocks when the kernel's rate
+    allows, else the largest power of two that fits (stated in `workload`)."""
+    import numpy as np
+    bs = 262144
+    base_n = 256
+    host = chk.datagen(base_n * bs, 0.5, 0.0, 4 + rank)
+    base = torch.from_numpy(host).to(dev)
+    bound = L.max_compressed_length(bs); stride = (bound + 15) // 16 * 16
+
+    def arena(nblk):
+        src = base.repeat((nblk + base_n - 1) // base_n)[: nblk * bs].contiguous() if nblk > base_n else base[: nblk * bs]
+        soff = torch.arange(nblk, device=dev, dtype=torch.int64) * bs
+        slen = torch.full((nblk,), bs, device=dev, dtype=torch.int32)
+        return src, soff, slen
+    # calibration on 2048 blocks (the compressed slots are reused modulo 4096 blocks: HC output is write-only here)
+    nslots = 4096
+    comp = torch.empty(nslots * stride, dtype=torch.uint8, device=dev)
+
+    def hc(nblk, src, soff, slen, clen):
+        for lo in range(0, nblk, nslots):
+            m = min(nslots, nblk - lo)
+            coff = torch.arange(m, device=dev, dtype=torch.int64) * stride
+            ccap = torch.full((m,), bound, device=dev, dtype=torch.int32)
+            L.batch.compress_hc_batch_dev(src, soff[lo:lo + m], slen[lo:lo + m], comp, coff, ccap, clen[lo:lo + m], 9)
+    src, soff, slen = arena(2048)
+    clen = torch.zeros(2048, device=dev, dtype=torch.int32)
+    tcal, _ = timed(lambda: hc(2048, src, soff, slen, clen), 1, 1, torch)
+    rate = 2048 * bs / tcal
+    want = args.hc_blocks
+    nblk = want
+    while nblk > 2048 and nblk * bs / rate > args.hc_seconds:
+        nblk //= 2
+    if world > 1:
+        nb = torch.tensor([nblk], device=dev, dtype=torch.int64); dist.all_reduce(nb, op=dist.ReduceOp.MIN); nblk = int(nb.item())
+    # the 64 GiB source does not fit beside nothing else only because of tiling cost: index the 64 MiB base by offsets instead
+    soff = (torch.arange(nblk, device=dev, dtype=torch.int64) % base_n) * bs
+    slen = torch.full((nblk,), bs, device=dev, dtype=torch.int32)
+    clen = torch.zeros(nblk, device=dev, dtype=torch.int32)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    if world > 1:
+        dist.barrier()
+    t, _ = timed(lambda: hc(nblk, base, soff, slen, clen), 1, 0, torch)
+    clocks = sampler.stop() if rank == 0 else None
+    csum = int(clen.sum().item())
+    if not bool((clen > 0).all().item()):
+        raise SystemExit("bench: config4 HC refused a block")
+    # sampled _ref check: the last sub-batch's first blocks decode with the reference, ratio of the reference on the same bytes
+    lo = (nblk - 1) // nslots * nslots
+    for k in range(0, min(4, nblk - lo)):
+        c = comp[k * stride: k * stride + int(clen[lo + k].item())].cpu().numpy()
+        b = int(soff[lo + k].item())
+        r, o = chk.decompress_safe(c, bs)
+        if r != bs or o != host[b:b + bs].tobytes():
+            raise SystemExit("bench: CPU checker rejects an HC block")
+    ref_c = sum(len(chk.compress_hc(host[i * bs:(i + 1) * bs], 9)) for i in range(16)) if hasattr(chk, "compress_hc") else None
+    ours16 = None
+    if ref_c:
+        c16 = torch.zeros(16, device=dev, dtype=torch.int32)
+        hc(16, base, torch.arange(16, device=dev, dtype=torch.int64) * bs, slen[:16], c16)
+        ours16 = 16 * bs / float(c16.sum().item())
+    (t,) = reduce_max(torch, dist, dev, world, t)
+    algo = nblk * bs + csum
+    del comp, base
+    torch.cuda.empty_cache()
+    return {"metric": "lz4_hc9_compress_256KiB_blocks", "value": nblk * bs * world / t / GIB, "unit": "GiB/s",
+            "workload": f"{nblk} x 256 KiB blocks per GPU (configs[3] states 262144 = 64 GiB on one GPU; "
+                        f"{'stated size' if nblk == want else 'largest power of two within the time budget of %d s' % args.hc_seconds}), "
+                        "LZ4_compress_HC level 9, RDG P=0.50, blocks addressed into a 64 MiB base corpus",
+            "blocks_per_gpu": nblk, "ratio": nblk * bs / csum, "reference_hc9_ratio_first16": (16 * bs / ref_c) if ref_c else None,
+            "ours_ratio_first16": ours16,
+            "roofline": {"bound": "hbm", "kernel": "lz4hc_compress_kernel<11,32>", "achieved": algo / t / 1e9, "peak": peak, "unit": "GB/s",
+                         "frac": algo / t / 1e9 / peak, "algorithmic_bytes_per_launch": algo,
+                         "note": "N + C; the kernel is latency-bound (one CTA per SM holds the 128 KiB candidate rings), the HBM fraction is tiny by construction"},
+            "clocks": clocks, "verified": "4 blocks re-decoded by the CPU checker; ratio next to LZ4_compress_HC(9) on the same 16 blocks"}
+
+
+def run_single_block(L, chk):
+    """What a caller who only swaps the factory gets: ONE 64 KiB block per call through b200lz4_compress_default /
+    b200lz4_decompress_safe / b200xxh64 (H2D + launch + D2H + sync each), next to the reference's own per-call time
+    (net_jpountz_lz4_LZ4JNI.c:75,216; XXHashJNI.c)."""
+    import numpy as np
+    lib = L._native.lib()
+    d = chk.datagen(BLOCK, 0.5, 0.0, 9)
+    c_ref = chk.compress(d.tobytes())
+    out = {}
+
+    def worker(nthreads, iters):
+        res = [None] * nthreads
+
+        def body(i):
+            src = d.copy(); bound = L.max_compressed_length(BLOCK)
+            comp = np.zeros(bound, dtype=np.uint8); back = np.zeros(BLOCK, dtype=np.uint8)
+            n = lib.b200lz4_compress_default(src.ctypes.data, comp.ctypes.data, BLOCK, bound)      # warm: context + staging
+            assert n > 0
+            t0 = time.perf_counter()
+            for _ in range(iters):
+                n = lib.b200lz4_compress_default(src.ctypes.data, comp.ctypes.data, BLOCK, bound)
+            t1 = time.perf_counter()
+            for _ in range(iters):
+                r = lib.b200lz4_decompress_safe(comp.ctypes.data, back.ctypes.data, n, BLOCK)
+            t2 = time.perf_counter()
+            for _ in range(iters):
+                h = lib.b200xxh64(src.ctypes.data, BLOCK, 0)
+            t3 = time.perf_counter()
+            assert r == BLOCK and (back == src).all() and (h & (2 ** 64 - 1)) == chk.xxh64(src, 0)
+            res[i] = ((t1 - t0) / iters, (t2 - t1) / iters, (t3 - t2) / iters)
+        ths = [threading.Thread(target=body, args=(i,)) for i in range(nthreads)]
+        for t in ths: t.start()
+        for t in ths: t.join()
+        return [sum(r[k] for r in res) / nthreads * 1e6 for k in range(3)]
+    for nt in (1, 16):
+        us = worker(nt, 200 if nt == 1 else 60)
+        out[f"threads_{nt}"] = {"compress_us_per_call": us[0], "decompress_safe_us_per_call": us[1], "xxh64_us_per_call": us[2],
+                                "compress_calls_per_s": nt * 1e6 / us[0], "decompress_calls_per_s": nt * 1e6 / us[1]}
+    # the reference's own functions, one thread, same block
+    t0 = time.perf_counter()
+    for _ in range(200):
+        chk.compress(d.tobytes())
+    tc = (time.perf_counter() - t0) / 200 * 1e6
+    t0 = time.perf_counter()
+    for _ in range(200):
+        chk.decompress_safe(c_ref, BLOCK)
+    td = (time.perf_counter() - t0) / 200 * 1e6
+    out["reference_one_thread"] = {"compress_us_per_call": tc, "decompress_safe_us_per_call": td,
+                                   "note": "through the Python checker binding (adds a few microseconds of its own)"}
+    out["note"] = ("one 64 KiB block per call = H2D + launch + D2H + two syncs: tens of microseconds of fixed cost, slower than the CPU; "
+                   "the batch entry points (LZ4B200Batch) are how the GPU pays off")
+    return out
+
+
+def run_e2e_multi(args, L, host, ngpus):
+    """ONE process (the JVM's shape) drives all GPUs: b200lz4_compress_fast_compact_host_multi then
+    b200lz4_decompress_fast_batch_host_multi over pinned host buffers, worker threads pinned to each GPU's NUMA node."""
+    import numpy as np
+    import torch
+    B = L.batch
+    n = min(args.e2e_blocks, args.blocks) * ngpus
+    room = host_memory_budget()
+    bound = L.max_compressed_length(BLOCK)
+    if room is not None:
+        fit = int(0.4 * room / (2 * BLOCK + bound + 16))
+        if fit < n:
+            n = max(4096 * ngpus, fit // (4096 * ngpus) * 4096 * ngpus)
+    nbytes = n * BLOCK
+    src_t = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    comp_t = torch.empty(n * ((bound + 15) // 16 * 16), dtype=torch.uint8).pin_memory()
+    out_t = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    src, comp, out = src_t.numpy(), comp_t.numpy(), out_t.numpy()
+    for lo in range(0, nbytes, len(host)):
+        hi = min(nbytes, lo + len(host)); src[lo:hi] = host[: hi - lo]
+    soff, slen = B.uniform_layout(n, BLOCK)
+    devs = list(range(ngpus))
+    best = 1e30
+    for k in range(3):
+        t0 = time.perf_counter()
+        ooff, olen, shard_base, shard_total = B.compress_fast_compact_host_multi(src, soff, slen, comp, devs, BLOCK)
+        res = B.decompress_fast_batch_host_multi(comp, ooff, olen, out, soff, slen, devs)
+        dt = time.perf_counter() - t0
+        if k:
+            best = min(best, dt)
+    assert (res == olen).all() and (out == src).all(), "e2e_multi round trip mismatch"
+    return {"value": nbytes / best / GIB, "unit": UNIT, "gpus": ngpus, "blocks": n,
+            "sample": f"{n} blocks from ONE process over {ngpus} GPUs: b200lz4_compress_fast_compact_host_multi + "
+                      "b200lz4_decompress_fast_batch_host_multi, pinned host buffers, wall clock, best of 2 after a warm-up call"}
+
+
 # ------------------------------------------------------------------------------------------ B200 arm
 def run_b200(args):
     import numpy as np
@@ -233,12 +565,12 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = numa_bind(local) if not args.no_numa else {"node": None, "note": "--no-numa"}
 
     import lz4java_b200 as L
     from oracle import oracle as O
     lib = L._native.lib()
     L._native.check(lib.b200lz4_set_device(local))
-    ctypes.c_int.in_dll(lib, "b200lz4_compress_hash_log").value = args.hash_log
     B = L.batch
 
     nblk = args.blocks                       # per GPU (weak scaling: every rank gets the same range size)
@@ -340,22 +672,39 @@ def run_b200(args):
     value = total_bytes / (t_step_ms / 1e3) / GIB
 
     # ---- end to end through the C ABI with HOST (pinned) buffers: H2D + kernels + D2H inside the timed region
+    del src, comp, v
+    torch.cuda.empty_cache()
     e2e = run_e2e(args, L, dev, host, rank, world)
 
+    # ---- the in-process multi-GPU API (one JVM, all GPUs), the secondary configurations, the one-block latency
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    e2e_multi = None
+    if world > 1 and not args.no_secondary:
+        if rank == 0:
+            try:
+                e2e_multi = run_e2e_multi(args, L, host, world)
+            except Exception as e:          # noqa: BLE001
+                e2e_multi = {"error": str(e)[:300]}
+        dist.barrier()
+    secondary = {}
+    if not args.no_secondary:
+        for key, fn in (("config5_xxh64", run_config5), ("config3_frame", run_config3), ("config4_hc9", run_config4)):
+            secondary[key] = fn(args, L, chk, torch, dist, dev, rank, world, local, peak)
+    single = run_single_block(L, chk) if (rank == 0 and not args.no_secondary) else None
+
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
         algo_bytes = nbytes + csum                                  # N + C per compress launch (this rank)
         achieved = algo_bytes / (t_comp_ms / 1e3) / 1e9
         traffic = None
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "compress_traffic.json")))
-            if tj.get("blocks") == nblk and tj.get("hash_log") == args.hash_log:
+            if tj.get("blocks") == nblk and tj.get("kernel", "").startswith("lz4_compress_wide"):
                 traffic = tj["dram_bytes_per_launch"]
         except Exception:
             pass
@@ -378,16 +727,18 @@ def run_b200(args):
             "dtype": "u8", "data": "synthetic",
             "config": {"workload": f"{nblk} x 64 KiB independent blocks per GPU (BASELINE configs[1]), "
                                    "fast compress + fast decompress, RDG_genBuffer P=0.50 tiled from 1 GiB",
-                       "blocks_per_gpu": nblk, "block_bytes": BLOCK, "hash_log": args.hash_log,
+                       "blocks_per_gpu": nblk, "block_bytes": BLOCK, "hash_log": 13, "numa": numa,
                        "l2": "inputs (64 GiB per GPU) larger than L2; no flush needed", "parallelism": f"range-shard x{world}"},
             "compress_gibs": total_bytes / (t_comp_ms / 1e3) / GIB,
             "decompress_gibs": total_bytes / (t_dec_ms / 1e3) / GIB,
             "ratio": total_bytes / total_comp,
-            "roofline": {"bound": "hbm", "kernel": f"lz4_compress_fast3_kernel<{args.hash_log},u16>", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "lz4_compress_wide_kernel<13> (3 warps per block)", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "frac_of_nominal_8TBs": achieved / 8000.0,
                          "traffic": traffic, "algorithmic_bytes_per_launch": algo_bytes, "peak_source": peak_src,
                          "decompress_achieved": algo_bytes / (t_dec_ms / 1e3) / 1e9},
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "cpu_baseline": cpu, "e2e": e2e, "e2e_multi": e2e_multi, "gpu_launches": launches, "clocks": clocks,
+            "config3_frame": secondary.get("config3_frame"), "config4_hc9": secondary.get("config4_hc9"),
+            "config5_xxh64": secondary.get("config5_xxh64"), "single_block": single,
             "verified": "xxh64 of every block before == after all steps; 3 blocks re-decoded by the CPU checker",
         }
         print(json.dumps(line), flush=True)
@@ -520,8 +871,13 @@ def main():
     ap.add_argument("--e2e-blocks", type=int, default=1 << 16, help="blocks per GPU per e2e step (4 GiB)")
     ap.add_argument("--cpu-blocks", type=int, default=1 << 14, help="blocks in the cpu_baseline sample (1 GiB)")
     ap.add_argument("--ref-blocks", type=int, default=1 << 15, help="blocks per step for --impl reference (2 GiB)")
-    ap.add_argument("--hash-log", type=int, default=13)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip configs[2..4], the one-block latency and the in-process multi-GPU leg")
+    ap.add_argument("--no-numa", action="store_true", help="do not pin the rank to its GPU's NUMA node")
+    ap.add_argument("--xxh-buffers", type=int, default=12_500_000, help="config 5: 4 KiB buffers per GPU")
+    ap.add_argument("--frames", type=int, default=32, help="config 3: 64 MiB frames per GPU")
+    ap.add_argument("--hc-blocks", type=int, default=1 << 18, help="config 4: 256 KiB blocks per GPU")
+    ap.add_argument("--hc-seconds", type=int, default=60, help="config 4: time budget of the timed pass")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

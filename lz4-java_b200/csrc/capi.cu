@@ -14,6 +14,10 @@
 #include <string>
 #include <thread>
 #include <vector>
+#if defined(__linux__) && !defined(B200_HOST_SIM)
+#include <sched.h>
+#define B200_HAVE_AFFINITY 1
+#endif
 
 namespace b200 {
 
@@ -394,6 +398,42 @@ static int one_block(Op op, const char* src, int src_len, char* dst, int dst_cap
     return res;
 }
 
+// Pin the calling WORKER thread to the CPUs of the NUMA node its GPU hangs off (sysfs: the PCI device's numa_node and the
+// node's cpulist).  Staging and descriptor buffers a worker allocates then land on that node (first touch), and its DMA
+// descriptors are written by a core next to the root complex.  Round 1's 8-GPU end-to-end run scaled 0.355 with every
+// thread floating over both sockets.  Best effort: any failure leaves the thread where it was.
+static void bind_worker_to_device_node(int device)
+{
+#ifdef B200_HAVE_AFFINITY
+    char bus[32] = "";
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) != cudaSuccess) return;
+    for (char* q = bus; *q; q++) if (*q >= 'A' && *q <= 'Z') *q = char(*q - 'A' + 'a');
+    char path[160];
+    snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus);
+    FILE* f = fopen(path, "r"); if (!f) return;
+    int node = -1; const int got = fscanf(f, "%d", &node); fclose(f);
+    if (got != 1 || node < 0) return;
+    snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+    f = fopen(path, "r"); if (!f) return;
+    char list[1024] = ""; const bool ok = fgets(list, sizeof list, f) != nullptr; fclose(f);
+    if (!ok) return;
+    cpu_set_t want; CPU_ZERO(&want);
+    for (char* q = list; *q; ) {                                   // "0-31,64-95"
+        char* e; const long a = strtol(q, &e, 10); if (e == q) break;
+        long b = a; q = e;
+        if (*q == '-') { b = strtol(q + 1, &e, 10); q = e; }
+        for (long c = a; c <= b && c < CPU_SETSIZE; c++) CPU_SET((int)c, &want);
+        if (*q == ',') q++; else break;
+    }
+    cpu_set_t cur;
+    if (sched_getaffinity(0, sizeof cur, &cur) != 0) return;
+    cpu_set_t both; CPU_AND(&both, &cur, &want);                   // never widen what the process was given (cgroups, taskset)
+    if (CPU_COUNT(&both) > 0) sched_setaffinity(0, sizeof both, &both);
+#else
+    (void)device;
+#endif
+}
+
 // ---- one process, several GPUs: contiguous block ranges, one worker thread (own device, own context) per GPU
 template <class ShardFn>
 static int run_sharded(size_t n, const int* devices, int ndev, ShardFn shard)
@@ -412,6 +452,7 @@ static int run_sharded(size_t n, const int* devices, int ndev, ShardFn shard)
         const size_t lo = n * (size_t)g / (size_t)ndev, hi = n * (size_t)(g + 1) / (size_t)ndev;
         if (hi == lo) return;
         int r = b200lz4_set_device(devices ? devices[g] : g);       // thread-local: this worker's device
+        if (r == 0 && g > 0) bind_worker_to_device_node(devices ? devices[g] : g);      // (shard 0 runs on the caller's thread: its affinity is the caller's business)
         if (r == 0) r = shard(lo, hi - lo);
         rc[(size_t)g] = r;
         if (r) msg[(size_t)g] = tl_err;
