@@ -296,9 +296,10 @@ def run_config5(args, L, chk, torch, dist, dev, rank, world, local, peak):
         sampler.start()
     if world > 1:
         dist.barrier()
-    t64, _ = timed(lambda: L.batch.xxh64_batch_dev(data, off, ln, o64, 0), 5, 3, torch)
-    t64b, _ = timed(lambda: L.batch.xxh64_batch_dev(data, off, ln, o64, 0x9747B28C), 5, 1, torch)
-    t32, _ = timed(lambda: L.batch.xxh32_batch_dev(data, off, ln, o32, 0x9747B28C), 5, 1, torch)
+    it = max(5, int(0.6 / max(n * 4104 / (peak * 1e9), 1e-4)))           # about 0.6 s per leg: the clock sampler needs that long
+    t64, _ = timed(lambda: L.batch.xxh64_batch_dev(data, off, ln, o64, 0), it, 3, torch)
+    t64b, _ = timed(lambda: L.batch.xxh64_batch_dev(data, off, ln, o64, 0x9747B28C), it, 1, torch)
+    t32, _ = timed(lambda: L.batch.xxh32_batch_dev(data, off, ln, o32, 0x9747B28C), it, 1, torch)
     clocks = sampler.stop() if rank == 0 else None
     import random
     rng = random.Random(5 + rank)
@@ -694,8 +695,10 @@ def run_b200(args):
     secondary = {}
     if not args.no_secondary:
         for key, fn in (("config5_xxh64", run_config5), ("config3_frame", run_config3), ("config4_hc9", run_config4)):
+            if args.only and key.split("_")[0] not in args.only.split(","):
+                continue
             secondary[key] = fn(args, L, chk, torch, dist, dev, rank, world, local, peak)
-    single = run_single_block(L, chk) if (rank == 0 and not args.no_secondary) else None
+    single = run_single_block(L, chk) if (rank == 0 and not args.no_secondary and not args.only) else None
 
     if rank == 0:
         peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
@@ -873,6 +876,7 @@ def main():
     ap.add_argument("--ref-blocks", type=int, default=1 << 15, help="blocks per step for --impl reference (2 GiB)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-secondary", action="store_true", help="skip configs[2..4], the one-block latency and the in-process multi-GPU leg")
+    ap.add_argument("--only", default="", help="development: run only these secondary configs, e.g. config3,config5")
     ap.add_argument("--no-numa", action="store_true", help="do not pin the rank to its GPU's NUMA node")
     ap.add_argument("--xxh-buffers", type=int, default=12_500_000, help="config 5: 4 KiB buffers per GPU")
     ap.add_argument("--frames", type=int, default=32, help="config 3: 64 MiB frames per GPU")

@@ -18,10 +18,12 @@
 #define B200_DYN_SMEM(name, al) uint8_t* name = simt::dyn_smem()
 #define B200_PREFETCH_L2(ptr) ((void)(ptr))
 #define B200_PREFETCH_L1(ptr) ((void)(ptr))
+#define B200_NANOSLEEP(ns) ((void)(ns))
 #else
 #define B200_DYN_SMEM(name, al) extern __shared__ __align__(al) uint8_t name[]
 #define B200_PREFETCH_L2(ptr) asm volatile("prefetch.global.L2 [%0];" :: "l"(__cvta_generic_to_global(ptr)))
 #define B200_PREFETCH_L1(ptr) asm volatile("prefetch.global.L1 [%0];" :: "l"(__cvta_generic_to_global(ptr)))
+#define B200_NANOSLEEP(ns) __nanosleep(ns)
 #endif
 
 namespace b200 {

@@ -9,7 +9,8 @@
 //      (block checksums)                                            -> xxh_batch_kernel<32>
 //   2. safe-decompress of every compressed block into its slot; stored blocks are copied
 //                                                                   -> lz4_decompress_safe_kernel, gather
-//   3. XXH32 over every frame's decoded content (content checksum)  -> xxh_batch_kernel<32>
+//   3. XXH32 over every frame's decoded content (content checksum)  -> xxh32_frames_chained_kernel: one warp per frame,
+//      beside the decoder on a second stream, taking each block as soon as it is decoded
 // Blocks of one frame are decoded in parallel because lz4-java only writes independent blocks
 // (LZ4FrameOutputStream.java:58,361-363; dependent blocks are rejected like the reference does).
 #include "../../include/b200lz4.h"
@@ -49,7 +50,9 @@ struct FrameIndex {
     size_t o_r_soff, o_r_doff, o_r_len;                              // raw blocks
     size_t o_h_off, o_h_len, o_h_out;                                // header descriptors
     size_t o_b_off, o_b_len, o_b_out;                                // block checksums
-    size_t o_f_off, o_f_len, o_f_out;                                // content checksums
+    size_t o_f_off, o_f_first, o_f_nblk, o_f_bs, o_f_out;            // content checksums (chained to the decoder: xxhash.cu)
+    size_t o_k_comp, o_k_rawlen;                                     // per block: index among the compressed blocks (-1: stored), stored size
+    cudaStream_t st2 = nullptr; cudaEvent_t e1 = nullptr, e2 = nullptr;   // the checksum warps run beside the decoder
     size_t n_comp = 0, n_raw = 0, n_bsum = 0, n_fsum = 0;
     std::vector<size_t> comp_ix, raw_ix, bsum_ix, fsum_ix;
 };
@@ -126,9 +129,19 @@ static int build_descriptors(FrameIndex& ix)
     ix.o_r_soff = put<uint64_t>(B, ix.n_raw);  ix.o_r_doff = put<uint64_t>(B, ix.n_raw); ix.o_r_len = put<int32_t>(B, ix.n_raw);
     ix.o_h_off = put<uint64_t>(B, nf); ix.o_h_len = put<int32_t>(B, nf); ix.o_h_out = put<uint32_t>(B, nf);
     ix.o_b_off = put<uint64_t>(B, ix.n_bsum); ix.o_b_len = put<int32_t>(B, ix.n_bsum); ix.o_b_out = put<uint32_t>(B, ix.n_bsum);
-    ix.o_f_off = put<uint64_t>(B, ix.n_fsum); ix.o_f_len = put<int32_t>(B, ix.n_fsum); ix.o_f_out = put<uint32_t>(B, ix.n_fsum);
+    ix.o_f_off = put<uint64_t>(B, ix.n_fsum); ix.o_f_first = put<uint32_t>(B, ix.n_fsum); ix.o_f_nblk = put<uint32_t>(B, ix.n_fsum);
+    ix.o_f_bs = put<uint32_t>(B, ix.n_fsum); ix.o_f_out = put<uint32_t>(B, ix.n_fsum);
+    ix.o_k_comp = put<int32_t>(B, ix.blocks.size()); ix.o_k_rawlen = put<int32_t>(B, ix.blocks.size());
     B.resize((B.size() + 15) & ~size_t(15));
     uint8_t* p = B.data();
+    for (size_t k = 0; k < ix.n_comp; k++) ((int32_t*)(p + ix.o_k_comp))[ix.comp_ix[k]] = (int32_t)k;
+    for (size_t k = 0; k < ix.n_raw; k++) { ((int32_t*)(p + ix.o_k_comp))[ix.raw_ix[k]] = -1; ((int32_t*)(p + ix.o_k_rawlen))[ix.raw_ix[k]] = (int32_t)ix.blocks[ix.raw_ix[k]].size; }
+    for (size_t k = 0; k < ix.n_fsum; k++) {
+        const FrameRec& fr = ix.frames[ix.fsum_ix[k]];
+        if (fr.first_block > 0xFFFFFFFFull || fr.nblocks > 0xFFFFFFFFull) return -10;
+        ((uint64_t*)(p + ix.o_f_off))[k] = fr.out_off; ((uint32_t*)(p + ix.o_f_first))[k] = (uint32_t)fr.first_block;
+        ((uint32_t*)(p + ix.o_f_nblk))[k] = (uint32_t)fr.nblocks; ((uint32_t*)(p + ix.o_f_bs))[k] = fr.bs;
+    }
     for (size_t k = 0; k < ix.n_comp; k++) {
         const BlockRec& b = ix.blocks[ix.comp_ix[k]];
         ((uint64_t*)(p + ix.o_c_soff))[k] = b.src_off; ((uint64_t*)(p + ix.o_c_doff))[k] = b.out_off;
@@ -169,6 +182,7 @@ void b200lz4f_index_free(void* index)
     FrameIndex* ix = (FrameIndex*)index;
     if (!ix) return;
     if (ix->d_blob) { cudaSetDevice(ix->device); cudaFree(ix->d_blob); }
+    if (ix->st2) { cudaSetDevice(ix->device); cudaStreamDestroy(ix->st2); cudaEventDestroy(ix->e1); cudaEventDestroy(ix->e2); }
     delete ix;
 }
 
@@ -184,14 +198,21 @@ int64_t b200lz4f_decode_dev(void* index, const uint8_t* d_src, uint8_t* d_slots,
     cudaStream_t st = (cudaStream_t)stream;
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return B200LZ4_E_NODEVICE;
+    if (ix.st2 && ix.device != dev) { cudaSetDevice(ix.device); cudaStreamDestroy(ix.st2); cudaEventDestroy(ix.e1); cudaEventDestroy(ix.e2); cudaSetDevice(dev); ix.st2 = nullptr; }
     if (!ix.d_blob || ix.device != dev) {
         if (ix.d_blob) { cudaSetDevice(ix.device); cudaFree(ix.d_blob); cudaSetDevice(dev); ix.d_blob = nullptr; }
         if (cudaMalloc(&ix.d_blob, ix.h_blob.size() + 16) != cudaSuccess) return B200LZ4_E_CUDA;
         ix.device = dev;
     }
+    if (!ix.st2) {
+        if (cudaStreamCreateWithFlags(&ix.st2, cudaStreamNonBlocking) != cudaSuccess) { ix.st2 = nullptr; return B200LZ4_E_CUDA; }
+        if (cudaEventCreateWithFlags(&ix.e1, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&ix.e2, cudaEventDisableTiming) != cudaSuccess)
+            return B200LZ4_E_CUDA;
+    }
     uint8_t* D = ix.d_blob; uint8_t* H = ix.h_blob.data();
     const size_t nf = ix.frames.size();
     if (cudaMemcpyAsync(D, H, ix.h_blob.size(), cudaMemcpyHostToDevice, st) != cudaSuccess) return B200LZ4_E_CUDA;
+    if (ix.n_comp && cudaMemsetAsync(D + ix.o_c_res, 0x80, ix.n_comp * 4, st) != cudaSuccess) return B200LZ4_E_CUDA;   // FRAME_RES_PENDING
     // 1. header + block checksums
     g_launch_count += 1;
     if (launch_xxh32(d_src, (uint64_t*)(D + ix.o_h_off), (int32_t*)(D + ix.o_h_len), 0, (uint32_t*)(D + ix.o_h_out), nf, st) != cudaSuccess) return B200LZ4_E_CUDA;
@@ -202,21 +223,31 @@ int64_t b200lz4f_decode_dev(void* index, const uint8_t* d_src, uint8_t* d_slots,
         if ((sum / ix.n_bsum >= XXH_LONG_AVG ? launch_xxh32_long : launch_xxh32)(
                 d_src, (uint64_t*)(D + ix.o_b_off), (int32_t*)(D + ix.o_b_len), 0, (uint32_t*)(D + ix.o_b_out), ix.n_bsum, st) != cudaSuccess) return B200LZ4_E_CUDA;
     }
-    // 2. blocks
+    // 2. stored blocks are copied, then every compressed block is decoded; 3. one warp per frame folds the blocks into the
+    // content checksum as the decoder hands them over (second stream; the decode kernel is launched FIRST and waits for nobody)
+    if (ix.n_raw) {
+        g_launch_count += 1;
+        if (launch_gather(d_src, (uint64_t*)(D + ix.o_r_soff), (int32_t*)(D + ix.o_r_len), d_slots, (uint64_t*)(D + ix.o_r_doff), ix.n_raw, st) != cudaSuccess) return B200LZ4_E_CUDA;
+    }
+    if (cudaEventRecord(ix.e1, st) != cudaSuccess) return B200LZ4_E_CUDA;
     if (ix.n_comp) {
         BatchArgs a{ d_src, (uint64_t*)(D + ix.o_c_soff), (int32_t*)(D + ix.o_c_slen), d_slots, (uint64_t*)(D + ix.o_c_doff),
                      (int32_t*)(D + ix.o_c_dcap), (int32_t*)(D + ix.o_c_res), ix.n_comp };
         g_launch_count += 1;
         if (launch_decompress_safe(a, st) != cudaSuccess) return B200LZ4_E_CUDA;
     }
-    if (ix.n_raw) {
+    if (ix.n_fsum) {
+        if (cudaStreamWaitEvent(ix.st2, ix.e1, 0) != cudaSuccess) return B200LZ4_E_CUDA;
         g_launch_count += 1;
-        if (launch_gather(d_src, (uint64_t*)(D + ix.o_r_soff), (int32_t*)(D + ix.o_r_len), d_slots, (uint64_t*)(D + ix.o_r_doff), ix.n_raw, st) != cudaSuccess) return B200LZ4_E_CUDA;
+        if (launch_xxh32_frames_chained(d_slots, (uint64_t*)(D + ix.o_f_off), (uint32_t*)(D + ix.o_f_first), (uint32_t*)(D + ix.o_f_nblk),
+                                        (uint32_t*)(D + ix.o_f_bs), (int32_t*)(D + ix.o_k_comp), (int32_t*)(D + ix.o_k_rawlen),
+                                        (int32_t*)(D + ix.o_c_res), (uint32_t*)(D + ix.o_f_out), ix.n_fsum, ix.st2) != cudaSuccess) return B200LZ4_E_CUDA;
+        if (cudaEventRecord(ix.e2, ix.st2) != cudaSuccess || cudaStreamWaitEvent(st, ix.e2, 0) != cudaSuccess) return B200LZ4_E_CUDA;
     }
-    // sizes come back; content-checksum descriptors depend on them
-    if (cudaMemcpyAsync(H + ix.o_c_res, D + ix.o_c_res, ix.n_comp * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) return B200LZ4_E_CUDA;
+    if (ix.n_comp && cudaMemcpyAsync(H + ix.o_c_res, D + ix.o_c_res, ix.n_comp * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) return B200LZ4_E_CUDA;
     if (cudaMemcpyAsync(H + ix.o_h_out, D + ix.o_h_out, nf * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) return B200LZ4_E_CUDA;
     if (ix.n_bsum && cudaMemcpyAsync(H + ix.o_b_out, D + ix.o_b_out, ix.n_bsum * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) return B200LZ4_E_CUDA;
+    if (ix.n_fsum && cudaMemcpyAsync(H + ix.o_f_out, D + ix.o_f_out, ix.n_fsum * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) return B200LZ4_E_CUDA;
     if (cudaStreamSynchronize(st) != cudaSuccess) return B200LZ4_E_CUDA;
 
     for (size_t f = 0; f < nf; f++)
@@ -245,27 +276,9 @@ int64_t b200lz4f_decode_dev(void* index, const uint8_t* d_src, uint8_t* d_slots,
         if (frame_len) frame_len[f] = len;
         total += (int64_t)len;
     }
-    if (gaps) return -11;
-    // 3. content checksums over each frame's (contiguous) content
-    if (ix.n_fsum) {
-        uint64_t sum = 0;
-        for (size_t k = 0; k < ix.n_fsum; k++) {
-            const FrameRec& fr = ix.frames[ix.fsum_ix[k]];
-            uint64_t len = 0; for (size_t j = 0; j < fr.nblocks; j++) len += (uint64_t)blen[fr.first_block + j];
-            if (len > 0x7FFFFFFFull) return -10;                              // >2 GiB frames are not indexed as one buffer
-            sum += len;
-            ((uint64_t*)(H + ix.o_f_off))[k] = fr.out_off; ((int32_t*)(H + ix.o_f_len))[k] = (int32_t)len;
-        }
-        if (cudaMemcpyAsync(D + ix.o_f_off, H + ix.o_f_off, ix.n_fsum * 8, cudaMemcpyHostToDevice, st) != cudaSuccess) return B200LZ4_E_CUDA;
-        if (cudaMemcpyAsync(D + ix.o_f_len, H + ix.o_f_len, ix.n_fsum * 4, cudaMemcpyHostToDevice, st) != cudaSuccess) return B200LZ4_E_CUDA;
-        g_launch_count += 1;
-        if ((sum / ix.n_fsum >= XXH_LONG_AVG ? launch_xxh32_long : launch_xxh32)(
-                d_slots, (uint64_t*)(D + ix.o_f_off), (int32_t*)(D + ix.o_f_len), 0, (uint32_t*)(D + ix.o_f_out), ix.n_fsum, st) != cudaSuccess) return B200LZ4_E_CUDA;
-        if (cudaMemcpyAsync(H + ix.o_f_out, D + ix.o_f_out, ix.n_fsum * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) return B200LZ4_E_CUDA;
-        if (cudaStreamSynchronize(st) != cudaSuccess) return B200LZ4_E_CUDA;
-        for (size_t k = 0; k < ix.n_fsum; k++)
-            if (((uint32_t*)(H + ix.o_f_out))[k] != ix.frames[ix.fsum_ix[k]].content_checksum) return -7;   // (:266-269)
-    }
+    if (gaps) return -11;                                   // (the chained checksum assumed contiguous content: the host path re-checks)
+    for (size_t k = 0; k < ix.n_fsum; k++)
+        if (((uint32_t*)(H + ix.o_f_out))[k] != ix.frames[ix.fsum_ix[k]].content_checksum) return -7;   // (:266-269)
     return total;
 }
 

@@ -315,7 +315,8 @@ lz4_decompress_safe_kernel(const uint8_t* __restrict__ src_base, const uint64_t*
 error:
     ret = -ip - 1;                                                                      // lz4.c:2337
 done:
-    if (lane == 0) result[b] = ret;
+    __syncwarp();
+    if (lane == 0) { __threadfence(); result[b] = ret; }   // the result word is also the block's "ready" flag (frame.cu chains the content hash to it)
 }
 
 // LZ4_decompress_fast: knows the exact decoded size, trusts the input (lz4.c:1794-1891); every

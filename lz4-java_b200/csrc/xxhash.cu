@@ -310,6 +310,65 @@ cudaError_t launch_xxh32_long(const uint8_t* base, const uint64_t* off, const in
 }
 #endif
 
+// ------------------------------------------------------------------ frame content checksums, chained to the block decoder
+// LZ4FrameInputStream verifies a frame's content XXH32 after its last block (LZ4FrameInputStream.java:264-273).  As a
+// second pass over 32 frames of 64 MiB it costs as much as decoding them (a stream is four serial chains, ~3 GB/s, however
+// many SMs idle).  Here one warp per frame runs WHILE the blocks are decoded (another stream, same device): it takes the
+// frame's blocks in order, spins on the decoder's per-block result word until that block is there (the decoder publishes it
+// behind a __threadfence), and folds the block in.  The decode kernel is launched first and never waits for this one.
+//   blk_comp[b] >= 0: index of block b in the decoder's result array;  < 0: stored block of blk_rawlen[b] bytes, already in place.
+//   c_res[k] == FRAME_RES_PENDING until block k is decoded; a negative result ends the frame's hash (the host reports -6).
+__global__ void __launch_bounds__(32)
+xxh32_frames_chained_kernel(const uint8_t* __restrict__ slots, const uint64_t* __restrict__ f_out_off, const uint32_t* __restrict__ f_first,
+                            const uint32_t* __restrict__ f_nblk, const uint32_t* __restrict__ f_bs,
+                            const int32_t* __restrict__ blk_comp, const int32_t* __restrict__ blk_rawlen,
+                            const int32_t* c_res, uint32_t* __restrict__ out, uint32_t n)
+{
+    const uint32_t f = blockIdx.x;
+    if (f >= n) return;
+    const int lane = lane_id();
+    const uint8_t* base = slots + f_out_off[f];
+    const uint32_t first = f_first[f], nblk = f_nblk[f], bs = f_bs[f];
+    uint32_t v = xxh32_chain_init(0u, lane);
+    uint64_t total = 0; uint32_t carry = 0;                 // bytes of the content seen so far; bytes of an unfinished stripe
+    bool big = false;                                       // at least one full stripe went through the chains
+    const uint8_t* tail = base; uint32_t rem = 0;
+    for (uint32_t k = 0; k < nblk; k++) {
+        const int32_t ci = blk_comp[first + k];
+        int32_t len;
+        if (ci < 0) len = blk_rawlen[first + k];
+        else {
+            const volatile int32_t* w = c_res + ci;
+            int32_t r = 0;
+            if (lane == 0) { while ((r = *w) == FRAME_RES_PENDING) { B200_NANOSLEEP(256); } }
+            len = __shfl_sync(B200_FULL, r, 0);
+            __threadfence();                                // the block's bytes were written before its result word
+            if (len < 0) break;
+        }
+        const uint8_t* p = base + size_t(k) * bs;
+        // blocks of a contiguous frame are full (a multiple of 16) except the last one; anything else makes the host answer -11
+        if (carry) break;
+        const size_t stripes = size_t(uint32_t(len)) >> 4;
+        if (stripes) { v = xxh32_warp_stripes(v, p, stripes, lane); big = true; }
+        carry = uint32_t(len) & 15u;
+        tail = p + 16 * stripes; rem = carry;
+        total += uint32_t(len);
+    }
+    const uint32_t h = big ? xxh32_chain_merge(v) : 0u + P32_5;
+    if (lane == 0) out[f] = finish32(h + uint32_t(total), tail, rem);
+}
+
+#ifndef B200_HOST_SIM
+cudaError_t launch_xxh32_frames_chained(const uint8_t* slots, const uint64_t* f_out_off, const uint32_t* f_first, const uint32_t* f_nblk,
+                                        const uint32_t* f_bs, const int32_t* blk_comp, const int32_t* blk_rawlen, const int32_t* c_res,
+                                        uint32_t* out, size_t n, cudaStream_t st)
+{
+    if (n == 0) return cudaSuccess;
+    xxh32_frames_chained_kernel<<<(unsigned)n, 32, 0, st>>>(slots, f_out_off, f_first, f_nblk, f_bs, blk_comp, blk_rawlen, c_res, out, (uint32_t)n);
+    return cudaGetLastError();
+}
+#endif
+
 // ---- the same for XXH64: stripes of 32 bytes, rows of 256 bytes (one 64-bit word per lane), chain = lane & 3.
 __device__ __forceinline__ uint64_t xxh64_chain_init(uint64_t seed, int lane)
 {
