@@ -13,7 +13,7 @@ def main(path, out, blocks, hash_log, label):
         m[r["Metric Name"]] = v * scale
         kern = r["Kernel Name"]
     rd, wr = m["dram__bytes_read.sum"], m["dram__bytes_write.sum"]
-    j = {"blocks": int(blocks), "hash_log": int(hash_log), "kernel": label, "kernel_name": kern[:80],
+    j = {"blocks": int(blocks), "kernel": label, "kernel_name": kern[:80],
          "dram_bytes_per_launch": int(rd + wr), "dram_read_bytes": int(rd), "dram_write_bytes": int(wr),
          "duration_ns_under_ncu": int(m["gpu__time_duration.sum"]),
          "smsp_inst_executed": int(m["smsp__inst_executed.sum"]),
