@@ -42,7 +42,7 @@ def main(seed, minutes):
         f.restype = ctypes.c_int; f.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
     cmp_ = T._build("comp_harness.cpp", f"libcompsim_{seed}.so")
     cmp_.sim_compress_fast.restype = ctypes.c_int
-    cmp_.sim_compress_fast.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int] + [ctypes.c_int] * 5
+    cmp_.sim_compress_fast.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
     t_end = time.time() + minutes * 60
     stats = {"decodes": 0, "malformed": 0, "compress": 0}
     while time.time() < t_end:
@@ -69,12 +69,12 @@ def main(seed, minutes):
                 assert r == want and (want < 0 or o == out), ("fast-malformed", b, seed, r, want, m.hex() if len(m) < 600 else len(m))
             stats["malformed"] += 4
         if len(d) <= 66000:
-            for variant in rng.sample(list(T.COMPRESS_VARIANTS), 3):
-                if T.COMPRESS_VARIANTS[variant][2] and len(d) >= 65536 + 11: continue
+            for variant in list(T.COMPRESS_KINDS):
+                if variant != "long" and len(d) >= 65536 + 11: continue
                 bound = chk.compress_bound(len(d))
-                cap = rng.choice([bound, bound, rng.randrange(0, bound + 1), len(c), max(0, len(c) - 1)])
-                r, cc = T.run_compress(cmp_, d, cap, variant)
-                assert 0 <= r <= cap, (variant, seed, len(d), cap, r)
+                cap = rng.choice([bound, bound, rng.randrange(0, bound + 1), len(c), max(0, len(c) - 1), -1])
+                r, cc = T.run_compress(cmp_, d, cap, variant, shift=rng.randrange(4))
+                assert 0 <= r <= max(cap, 0), (variant, seed, len(d), cap, r)
                 if r > 0:
                     rr, o = chk.decompress_safe(cc, len(d))
                     assert rr == len(d) and o == d, ("compress", variant, seed, len(d), cap)
