@@ -186,11 +186,17 @@ int b200xxh64_batch_host_multi(const uint8_t* base, const uint64_t* off, const i
  * XXH32 checksums and decodes all blocks of all frames in batched launches.
  * Error codes (negative): -1 premature end, -2 bad magic, -3 descriptor checksum, -4 block larger than the
  * frame's maximum, -5 block checksum, -6 block decode error, -7 content checksum, -8 content size,
- * -9 dst too small, -10 unsupported descriptor, -11 (decode_dev only) a short block in mid-frame. */
+ * -9 dst too small, -10 unsupported descriptor, -11 (decode_dev only) every check passed but a frame has a short block
+ * before its last one (flush()), so its content is not one run inside d_slots: read block b at block_off[b] for
+ * block_len_out[b] bytes (b200lz4f_index_block_offsets).
+ * d_slots layout: a full block takes blockMaxSize bytes; a block that cannot fill it (a stored block, or a compressed one
+ * of fewer than blockMaxSize/255 bytes) takes what it can decode to, rounded up to 16 -- slot_bytes does not grow with
+ * blockMaxSize for a stream of tiny blocks. */
 int64_t b200lz4f_decompress_host(const uint8_t* src, size_t srcSize, uint8_t* dst, size_t dstCapacity);
 void*   b200lz4f_index_create(const uint8_t* src_host, size_t srcSize, uint64_t* slot_bytes, int* err);
 size_t  b200lz4f_index_frames(void* index);
 size_t  b200lz4f_index_blocks(void* index);
+void    b200lz4f_index_block_offsets(void* index, uint64_t* block_off);   /* b200lz4f_index_blocks() entries, bytes into d_slots */
 int64_t b200lz4f_decode_dev(void* index, const uint8_t* d_src, uint8_t* d_slots, uint64_t* frame_off, uint64_t* frame_len,
                             int32_t* block_len_out, void* stream);
 void    b200lz4f_index_free(void* index);
@@ -206,7 +212,11 @@ size_t  b200lz4f_compress_bound(size_t srcSize, int bsCode);
 int64_t b200lz4f_compress_host(const uint8_t* src, size_t srcSize, uint8_t* dst, size_t dstCapacity, int bsCode, int flags);
 size_t  b200lz4block_compress_bound(size_t srcSize, int blockSize);
 int64_t b200lz4block_compress_host(const uint8_t* src, size_t srcSize, uint8_t* dst, size_t dstCapacity, int blockSize);
-int64_t b200lz4block_decompress_host(const uint8_t* src, size_t srcSize, uint8_t* dst, size_t dstCapacity);
+/* stopOnEmptyBlock: LZ4BlockInputStream's constructor flag (LZ4BlockInputStream.java:60-72; its default is true): non-zero
+ * ends at the first empty block and reports in *srcConsumed (may be NULL) how far it read; zero steps over empty blocks and
+ * reads concatenated streams to the end of src. */
+int64_t b200lz4block_decompress_host(const uint8_t* src, size_t srcSize, uint8_t* dst, size_t dstCapacity,
+                                     int stopOnEmptyBlock, size_t* srcConsumed);
 int     b200lz4_compress_with_length(const char* src, char* dst, int srcSize, int dstCapacity);
 int     b200lz4_decompressed_length(const char* src);
 int     b200lz4_decompress_with_length(const char* src, int srcAvail, char* dst, int dstCapacity);

@@ -131,15 +131,18 @@ int64_t b200lz4block_compress_host(const uint8_t* src, size_t n, uint8_t* dst, s
     return (int64_t)o;
 }
 
-// Decodes one LZ4Block stream (up to and including its empty end block; concatenated streams continue,
-// like stopOnEmptyBlock=false).  Returns decoded bytes; -1 premature end, -2 "Stream is corrupted", -9 dst too small.
-int64_t b200lz4block_decompress_host(const uint8_t* src, size_t n, uint8_t* dst, size_t cap)
+// Decodes an LZ4Block stream the way LZ4BlockInputStream reads it.  stopOnEmptyBlock != 0 (the reference's default, :100-104):
+// reading ends at the first empty block, whatever follows is left alone (*srcConsumed says where), and a stream that ends
+// before one is "Stream ended prematurely" (:192-198).  stopOnEmptyBlock == 0: empty blocks are stepped over, concatenated
+// streams continue, and the end of src at (or inside) a header ends the stream quietly (:193-194, tryReadFully).
+// Returns decoded bytes; -1 premature end, -2 "Stream is corrupted", -9 dst too small.
+int64_t b200lz4block_decompress_host(const uint8_t* src, size_t n, uint8_t* dst, size_t cap, int stopOnEmptyBlock, size_t* srcConsumed)
 {
     std::vector<uint64_t> soff, doff; std::vector<int32_t> savail, dlen, csz; std::vector<uint32_t> want;
     std::vector<uint64_t> hoff; std::vector<int32_t> hlen;
     size_t ip = 0, op = 0;
-    while (ip < n) {                                                             // refill (:191-264)
-        if (n - ip < LZ4BLOCK_HEADER) return -1;
+    for (;;) {                                                                   // refill (:191-264)
+        if (n - ip < LZ4BLOCK_HEADER) { if (stopOnEmptyBlock) return -1; ip = n; break; }
         if (memcmp(src + ip, LZ4BLOCK_MAGIC, 8) != 0) return -2;
         const int token = src[ip + 8], method = token & 0xF0, level = 10 + (token & 0x0F);
         if (method != METHOD_RAW && method != METHOD_LZ4) return -2;
@@ -148,7 +151,7 @@ int64_t b200lz4block_decompress_host(const uint8_t* src, size_t n, uint8_t* dst,
         if (olen > (1 << level) || olen < 0 || clen < 0 || (olen == 0 && clen != 0) || (olen != 0 && clen == 0) ||
             (method == METHOD_RAW && olen != clen)) return -2;
         ip += LZ4BLOCK_HEADER;
-        if (olen == 0) { if (check != 0) return -2; continue; }                  // empty block: end of one stream
+        if (olen == 0) { if (check != 0) return -2; if (stopOnEmptyBlock) break; continue; }   // empty block (:225-233)
         if (n - ip < (size_t)clen) return -1;
         if (cap - op < (size_t)olen) return -9;
         if (method == METHOD_RAW) memcpy(dst + op, src + ip, (size_t)olen);
@@ -168,6 +171,7 @@ int64_t b200lz4block_decompress_host(const uint8_t* src, size_t n, uint8_t* dst,
         if (rc) return rc;
         for (size_t i = 0; i < sums.size(); i++) if ((sums[i] & 0x0FFFFFFFu) != want[i]) return -2;
     }
+    if (srcConsumed) *srcConsumed = ip;
     return (int64_t)op;
 }
 

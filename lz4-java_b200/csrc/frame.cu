@@ -35,7 +35,7 @@ struct FrameRec {
 };
 static constexpr uint64_t XXH_LONG_AVG = 32768;     // average stream length from which a whole warp per stream wins
 
-struct BlockRec { uint64_t src_off; uint32_t size; bool raw; uint32_t checksum; bool has_checksum; size_t frame; uint64_t out_off; };
+struct BlockRec { uint64_t src_off; uint32_t size; bool raw; uint32_t checksum; bool has_checksum; size_t frame; uint64_t out_off; uint32_t cap; };
 
 struct FrameIndex {
     std::vector<FrameRec> frames;
@@ -50,8 +50,8 @@ struct FrameIndex {
     size_t o_r_soff, o_r_doff, o_r_len;                              // raw blocks
     size_t o_h_off, o_h_len, o_h_out;                                // header descriptors
     size_t o_b_off, o_b_len, o_b_out;                                // block checksums
-    size_t o_f_off, o_f_first, o_f_nblk, o_f_bs, o_f_out;            // content checksums (chained to the decoder: xxhash.cu)
-    size_t o_k_comp, o_k_rawlen;                                     // per block: index among the compressed blocks (-1: stored), stored size
+    size_t o_f_first, o_f_nblk, o_f_out;                                        // content checksums (chained to the decoder: xxhash.cu)
+    size_t o_k_comp, o_k_rawlen, o_k_off;                            // per block: index among the compressed blocks (-1: stored), stored size, slot
     cudaStream_t st2 = nullptr; cudaEvent_t e1 = nullptr, e2 = nullptr;   // the checksum warps run beside the decoder
     size_t n_comp = 0, n_raw = 0, n_bsum = 0, n_fsum = 0;
     std::vector<size_t> comp_ix, raw_ix, bsum_ix, fsum_ix;
@@ -96,7 +96,12 @@ static int index_frames(const uint8_t* src, size_t n, FrameIndex& ix)
             ip += sz;
             b.has_checksum = f.flg & 0x10;
             if (b.has_checksum) { if (n - ip < 4) return -1; b.checksum = rd32(src + ip); ip += 4; }
-            b.out_off = ix.slot_bytes; ix.slot_bytes += f.bs;
+            // the slot: a stored block needs its own size, a compressed one cannot decode to more than 255 bytes per byte
+            // (one length byte adds at most 255) -- so a stream of tiny flushed blocks asks for what it can fill, not for
+            // blockMaxSize each.  Full blocks keep exactly bs: a frame without short blocks in the middle stays contiguous.
+            const uint64_t room = b.raw ? sz : std::min<uint64_t>(f.bs, 255ull * sz);
+            b.cap = (uint32_t)room;
+            b.out_off = ix.slot_bytes; ix.slot_bytes += room >= f.bs ? f.bs : ((room + 15) & ~15ull);
             ix.blocks.push_back(b);
         }
         f.nblocks = ix.blocks.size() - f.first_block;
@@ -129,23 +134,23 @@ static int build_descriptors(FrameIndex& ix)
     ix.o_r_soff = put<uint64_t>(B, ix.n_raw);  ix.o_r_doff = put<uint64_t>(B, ix.n_raw); ix.o_r_len = put<int32_t>(B, ix.n_raw);
     ix.o_h_off = put<uint64_t>(B, nf); ix.o_h_len = put<int32_t>(B, nf); ix.o_h_out = put<uint32_t>(B, nf);
     ix.o_b_off = put<uint64_t>(B, ix.n_bsum); ix.o_b_len = put<int32_t>(B, ix.n_bsum); ix.o_b_out = put<uint32_t>(B, ix.n_bsum);
-    ix.o_f_off = put<uint64_t>(B, ix.n_fsum); ix.o_f_first = put<uint32_t>(B, ix.n_fsum); ix.o_f_nblk = put<uint32_t>(B, ix.n_fsum);
-    ix.o_f_bs = put<uint32_t>(B, ix.n_fsum); ix.o_f_out = put<uint32_t>(B, ix.n_fsum);
+    ix.o_f_first = put<uint32_t>(B, ix.n_fsum); ix.o_f_nblk = put<uint32_t>(B, ix.n_fsum); ix.o_f_out = put<uint32_t>(B, ix.n_fsum);
     ix.o_k_comp = put<int32_t>(B, ix.blocks.size()); ix.o_k_rawlen = put<int32_t>(B, ix.blocks.size());
+    ix.o_k_off = put<uint64_t>(B, ix.blocks.size());
     B.resize((B.size() + 15) & ~size_t(15));
     uint8_t* p = B.data();
+    for (size_t k = 0; k < ix.blocks.size(); k++) ((uint64_t*)(p + ix.o_k_off))[k] = ix.blocks[k].out_off;
     for (size_t k = 0; k < ix.n_comp; k++) ((int32_t*)(p + ix.o_k_comp))[ix.comp_ix[k]] = (int32_t)k;
     for (size_t k = 0; k < ix.n_raw; k++) { ((int32_t*)(p + ix.o_k_comp))[ix.raw_ix[k]] = -1; ((int32_t*)(p + ix.o_k_rawlen))[ix.raw_ix[k]] = (int32_t)ix.blocks[ix.raw_ix[k]].size; }
     for (size_t k = 0; k < ix.n_fsum; k++) {
         const FrameRec& fr = ix.frames[ix.fsum_ix[k]];
         if (fr.first_block > 0xFFFFFFFFull || fr.nblocks > 0xFFFFFFFFull) return -10;
-        ((uint64_t*)(p + ix.o_f_off))[k] = fr.out_off; ((uint32_t*)(p + ix.o_f_first))[k] = (uint32_t)fr.first_block;
-        ((uint32_t*)(p + ix.o_f_nblk))[k] = (uint32_t)fr.nblocks; ((uint32_t*)(p + ix.o_f_bs))[k] = fr.bs;
+        ((uint32_t*)(p + ix.o_f_first))[k] = (uint32_t)fr.first_block; ((uint32_t*)(p + ix.o_f_nblk))[k] = (uint32_t)fr.nblocks;
     }
     for (size_t k = 0; k < ix.n_comp; k++) {
         const BlockRec& b = ix.blocks[ix.comp_ix[k]];
         ((uint64_t*)(p + ix.o_c_soff))[k] = b.src_off; ((uint64_t*)(p + ix.o_c_doff))[k] = b.out_off;
-        ((int32_t*)(p + ix.o_c_slen))[k] = (int32_t)b.size; ((int32_t*)(p + ix.o_c_dcap))[k] = (int32_t)ix.frames[b.frame].bs;
+        ((int32_t*)(p + ix.o_c_slen))[k] = (int32_t)b.size; ((int32_t*)(p + ix.o_c_dcap))[k] = (int32_t)b.cap;
     }
     for (size_t k = 0; k < ix.n_raw; k++) {
         const BlockRec& b = ix.blocks[ix.raw_ix[k]];
@@ -186,11 +191,11 @@ void b200lz4f_index_free(void* index)
     delete ix;
 }
 
-// Decode every indexed frame: d_src holds the container bytes, d_slots (>= slot_bytes) receives block k
-// of frame f at frames[f].out_off + k*blockMaxSize.  On success frame_off[f] / frame_len[f] (host
-// arrays, may be NULL) describe each frame's content, contiguous inside d_slots when no block was
-// flushed short mid-frame (otherwise -11 is returned: caller should use the host path, which
-// stitches runs).  Returns total decoded bytes or a negative code.
+// Decode every indexed frame: d_src holds the container bytes, d_slots (>= slot_bytes) receives block b at its slot
+// (b200lz4f_index_block_offsets; full blocks of one frame lie back to back).  On success frame_off[f] / frame_len[f] (host
+// arrays, may be NULL) describe each frame's content, one run inside d_slots when no block was flushed short mid-frame;
+// otherwise -11 is returned after every check has passed and the caller reads block by block (the host path below does).
+// Returns total decoded bytes or a negative code.
 int64_t b200lz4f_decode_dev(void* index, const uint8_t* d_src, uint8_t* d_slots, uint64_t* frame_off, uint64_t* frame_len,
                             int32_t* block_len_out, void* stream)
 {
@@ -239,8 +244,8 @@ int64_t b200lz4f_decode_dev(void* index, const uint8_t* d_src, uint8_t* d_slots,
     if (ix.n_fsum) {
         if (cudaStreamWaitEvent(ix.st2, ix.e1, 0) != cudaSuccess) return B200LZ4_E_CUDA;
         g_launch_count += 1;
-        if (launch_xxh32_frames_chained(d_slots, (uint64_t*)(D + ix.o_f_off), (uint32_t*)(D + ix.o_f_first), (uint32_t*)(D + ix.o_f_nblk),
-                                        (uint32_t*)(D + ix.o_f_bs), (int32_t*)(D + ix.o_k_comp), (int32_t*)(D + ix.o_k_rawlen),
+        if (launch_xxh32_frames_chained(d_slots, (uint64_t*)(D + ix.o_k_off), (uint32_t*)(D + ix.o_f_first), (uint32_t*)(D + ix.o_f_nblk),
+                                        (int32_t*)(D + ix.o_k_comp), (int32_t*)(D + ix.o_k_rawlen),
                                         (int32_t*)(D + ix.o_c_res), (uint32_t*)(D + ix.o_f_out), ix.n_fsum, ix.st2) != cudaSuccess) return B200LZ4_E_CUDA;
         if (cudaEventRecord(ix.e2, ix.st2) != cudaSuccess || cudaStreamWaitEvent(st, ix.e2, 0) != cudaSuccess) return B200LZ4_E_CUDA;
     }
@@ -276,14 +281,18 @@ int64_t b200lz4f_decode_dev(void* index, const uint8_t* d_src, uint8_t* d_slots,
         if (frame_len) frame_len[f] = len;
         total += (int64_t)len;
     }
-    if (gaps) return -11;                                   // (the chained checksum assumed contiguous content: the host path re-checks)
     for (size_t k = 0; k < ix.n_fsum; k++)
         if (((uint32_t*)(H + ix.o_f_out))[k] != ix.frames[ix.fsum_ix[k]].content_checksum) return -7;   // (:266-269)
-    return total;
+    return gaps ? -11 : total;                              // -11: everything verified, but read the blocks one by one
 }
 
 size_t b200lz4f_index_frames(void* index) { return ((FrameIndex*)index)->frames.size(); }
 size_t b200lz4f_index_blocks(void* index) { return ((FrameIndex*)index)->blocks.size(); }
+void b200lz4f_index_block_offsets(void* index, uint64_t* block_off)
+{
+    const FrameIndex& ix = *(FrameIndex*)index;
+    for (size_t b = 0; b < ix.blocks.size(); b++) block_off[b] = ix.blocks[b].out_off;
+}
 
 // Whole thing with HOST buffers: index, upload, decode, download frame by frame into one contiguous stream.
 int64_t b200lz4f_decompress_host(const uint8_t* src, size_t n, uint8_t* dst, size_t dst_capacity)
@@ -313,25 +322,27 @@ int64_t b200lz4f_decompress_host(const uint8_t* src, size_t n, uint8_t* dst, siz
                 pos += flen[f];
             }
         } else {
-            // general layout: copy block by block, then verify content checksums with a second pass over dst on the device
+            // short blocks in mid-frame (everything is verified already): the device packs the blocks, one copy brings them back
             rc = 0;
-            for (size_t b = 0; b < ix.blocks.size() && ok; b++) {
-                const uint64_t l = (uint64_t)blen[b];
-                if (pos + l > dst_capacity) { rc = -9; ok = false; break; }
-                if (l && cudaMemcpyAsync(dst + pos, d_slots + ix.blocks[b].out_off, l, cudaMemcpyDeviceToHost, st) != cudaSuccess) { rc = B200LZ4_E_CUDA; ok = false; }
-                pos += l;
-            }
-            if (ok && cudaStreamSynchronize(st) != cudaSuccess) { rc = B200LZ4_E_CUDA; ok = false; }
-            if (ok) {
-                uint64_t p2 = 0;
-                for (size_t f = 0; f < ix.frames.size() && ok; f++) {
-                    if (ix.frames[f].has_checksum) {
-                        if (flen[f] > 0x7FFFFFFFull) { rc = -10; ok = false; break; }
-                        if (b200xxh32(dst + p2, (size_t)flen[f], 0) != ix.frames[f].content_checksum) { rc = -7; ok = false; }
-                    }
-                    p2 += flen[f];
+            const size_t nb = ix.blocks.size();
+            std::vector<uint64_t> from(nb), to(nb);
+            for (size_t b = 0; b < nb; b++) { from[b] = ix.blocks[b].out_off; to[b] = pos; pos += (uint64_t)blen[b]; }
+            if (pos > dst_capacity) { rc = -9; ok = false; }
+            uint8_t* d_tmp = nullptr;
+            const size_t o_to = (nb * 8 + 15) & ~size_t(15), o_len = 2 * o_to, o_out = (o_len + nb * 4 + 15) & ~size_t(15);
+            if (ok && pos) {
+                if (cudaMalloc(&d_tmp, o_out + pos + 16) != cudaSuccess) { rc = B200LZ4_E_CUDA; ok = false; d_tmp = nullptr; }
+                if (ok && (cudaMemcpyAsync(d_tmp, from.data(), nb * 8, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+                           cudaMemcpyAsync(d_tmp + o_to, to.data(), nb * 8, cudaMemcpyHostToDevice, st) != cudaSuccess ||
+                           cudaMemcpyAsync(d_tmp + o_len, blen.data(), nb * 4, cudaMemcpyHostToDevice, st) != cudaSuccess)) { rc = B200LZ4_E_CUDA; ok = false; }
+                if (ok) {
+                    g_launch_count += 1;
+                    if (launch_gather(d_slots, (uint64_t*)d_tmp, (int32_t*)(d_tmp + o_len), d_tmp + o_out, (uint64_t*)(d_tmp + o_to), nb, st) != cudaSuccess ||
+                        cudaMemcpyAsync(dst, d_tmp + o_out, pos, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+                        cudaStreamSynchronize(st) != cudaSuccess) { rc = B200LZ4_E_CUDA; ok = false; }
                 }
             }
+            if (d_tmp) cudaFree(d_tmp);
         }
         if (ok) { if (cudaStreamSynchronize(st) != cudaSuccess) rc = B200LZ4_E_CUDA; else rc = (int64_t)pos; }
     } while (0);

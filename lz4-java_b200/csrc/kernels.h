@@ -34,8 +34,8 @@ cudaError_t launch_xxh32_long(const uint8_t* base, const uint64_t* off, const in
                               uint32_t* out, size_t n, cudaStream_t st);
 // frame content checksums chained to the block decoder (frame.cu): one warp per frame follows the decoder's result words
 static constexpr int32_t FRAME_RES_PENDING = int32_t(0x80808080);      // what cudaMemset(0x80) leaves; no decoder result looks like it
-cudaError_t launch_xxh32_frames_chained(const uint8_t* slots, const uint64_t* f_out_off, const uint32_t* f_first, const uint32_t* f_nblk,
-                                        const uint32_t* f_bs, const int32_t* blk_comp, const int32_t* blk_rawlen, const int32_t* c_res,
+cudaError_t launch_xxh32_frames_chained(const uint8_t* slots, const uint64_t* blk_off, const uint32_t* f_first, const uint32_t* f_nblk,
+                                        const int32_t* blk_comp, const int32_t* blk_rawlen, const int32_t* c_res,
                                         uint32_t* out, size_t n, cudaStream_t st);
 cudaError_t launch_xxh64(const uint8_t* base, const uint64_t* off, const int32_t* len, uint64_t seed,
                          uint64_t* out, size_t n, cudaStream_t st);

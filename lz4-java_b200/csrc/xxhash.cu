@@ -316,55 +316,64 @@ cudaError_t launch_xxh32_long(const uint8_t* base, const uint64_t* off, const in
 // many SMs idle).  Here one warp per frame runs WHILE the blocks are decoded (another stream, same device): it takes the
 // frame's blocks in order, spins on the decoder's per-block result word until that block is there (the decoder publishes it
 // behind a __threadfence), and folds the block in.  The decode kernel is launched first and never waits for this one.
-//   blk_comp[b] >= 0: index of block b in the decoder's result array;  < 0: stored block of blk_rawlen[b] bytes, already in place.
-//   c_res[k] == FRAME_RES_PENDING until block k is decoded; a negative result ends the frame's hash (the host reports -6).
+//   blk_off[b]: where block b lies in the slot layout;  blk_comp[b] >= 0: its index in the decoder's result array;  < 0: a
+//   stored block of blk_rawlen[b] bytes, already in place.  c_res[k] == FRAME_RES_PENDING until block k is decoded; a negative
+//   result ends the frame's hash (the host reports -6).  Blocks need not be full: the bytes of an unfinished 16-byte stripe
+//   wait in shared memory for the next block (a frame written with flush() calls has short blocks anywhere).
 __global__ void __launch_bounds__(32)
-xxh32_frames_chained_kernel(const uint8_t* __restrict__ slots, const uint64_t* __restrict__ f_out_off, const uint32_t* __restrict__ f_first,
-                            const uint32_t* __restrict__ f_nblk, const uint32_t* __restrict__ f_bs,
-                            const int32_t* __restrict__ blk_comp, const int32_t* __restrict__ blk_rawlen,
+xxh32_frames_chained_kernel(const uint8_t* __restrict__ slots, const uint64_t* __restrict__ blk_off, const uint32_t* __restrict__ f_first,
+                            const uint32_t* __restrict__ f_nblk, const int32_t* __restrict__ blk_comp, const int32_t* __restrict__ blk_rawlen,
                             const int32_t* c_res, uint32_t* __restrict__ out, uint32_t n)
 {
+    __shared__ __align__(16) uint8_t s_carry[16];
     const uint32_t f = blockIdx.x;
     if (f >= n) return;
     const int lane = lane_id();
-    const uint8_t* base = slots + f_out_off[f];
-    const uint32_t first = f_first[f], nblk = f_nblk[f], bs = f_bs[f];
+    const uint32_t first = f_first[f], nblk = f_nblk[f];
     uint32_t v = xxh32_chain_init(0u, lane);
-    uint64_t total = 0; uint32_t carry = 0;                 // bytes of the content seen so far; bytes of an unfinished stripe
+    uint64_t total = 0; uint32_t carry = 0;                 // bytes of the content seen so far; bytes waiting in s_carry
     bool big = false;                                       // at least one full stripe went through the chains
-    const uint8_t* tail = base; uint32_t rem = 0;
     for (uint32_t k = 0; k < nblk; k++) {
         const int32_t ci = blk_comp[first + k];
-        int32_t len;
-        if (ci < 0) len = blk_rawlen[first + k];
+        int32_t r;
+        if (ci < 0) r = blk_rawlen[first + k];
         else {
             const volatile int32_t* w = c_res + ci;
-            int32_t r = 0;
+            r = 0;
             if (lane == 0) { while ((r = *w) == FRAME_RES_PENDING) { B200_NANOSLEEP(256); } }
-            len = __shfl_sync(B200_FULL, r, 0);
+            r = __shfl_sync(B200_FULL, r, 0);
             __threadfence();                                // the block's bytes were written before its result word
-            if (len < 0) break;
+            if (r < 0) break;
         }
-        const uint8_t* p = base + size_t(k) * bs;
-        // blocks of a contiguous frame are full (a multiple of 16) except the last one; anything else makes the host answer -11
-        if (carry) break;
-        const size_t stripes = size_t(uint32_t(len)) >> 4;
+        const uint8_t* p = slots + blk_off[first + k];
+        uint32_t len = uint32_t(r);
+        total += len;
+        if (carry) {                                        // finish the stripe the previous block left open
+            const uint32_t t = min(16u - carry, len);
+            if (uint32_t(lane) < t) s_carry[carry + lane] = p[lane];
+            __syncwarp();
+            carry += t; p += t; len -= t;
+            if (carry < 16u) continue;
+            v = round32(v, reinterpret_cast<const uint32_t*>(s_carry)[lane & 3]); big = true; carry = 0;
+            __syncwarp();
+        }
+        const size_t stripes = size_t(len) >> 4;
         if (stripes) { v = xxh32_warp_stripes(v, p, stripes, lane); big = true; }
-        carry = uint32_t(len) & 15u;
-        tail = p + 16 * stripes; rem = carry;
-        total += uint32_t(len);
+        carry = len & 15u;
+        if (uint32_t(lane) < carry) s_carry[lane] = p[16 * stripes + lane];
+        __syncwarp();
     }
     const uint32_t h = big ? xxh32_chain_merge(v) : 0u + P32_5;
-    if (lane == 0) out[f] = finish32(h + uint32_t(total), tail, rem);
+    if (lane == 0) out[f] = finish32(h + uint32_t(total), s_carry, carry);
 }
 
 #ifndef B200_HOST_SIM
-cudaError_t launch_xxh32_frames_chained(const uint8_t* slots, const uint64_t* f_out_off, const uint32_t* f_first, const uint32_t* f_nblk,
-                                        const uint32_t* f_bs, const int32_t* blk_comp, const int32_t* blk_rawlen, const int32_t* c_res,
+cudaError_t launch_xxh32_frames_chained(const uint8_t* slots, const uint64_t* blk_off, const uint32_t* f_first, const uint32_t* f_nblk,
+                                        const int32_t* blk_comp, const int32_t* blk_rawlen, const int32_t* c_res,
                                         uint32_t* out, size_t n, cudaStream_t st)
 {
     if (n == 0) return cudaSuccess;
-    xxh32_frames_chained_kernel<<<(unsigned)n, 32, 0, st>>>(slots, f_out_off, f_first, f_nblk, f_bs, blk_comp, blk_rawlen, c_res, out, (uint32_t)n);
+    xxh32_frames_chained_kernel<<<(unsigned)n, 32, 0, st>>>(slots, blk_off, f_first, f_nblk, blk_comp, blk_rawlen, c_res, out, (uint32_t)n);
     return cudaGetLastError();
 }
 #endif

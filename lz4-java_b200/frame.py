@@ -75,10 +75,11 @@ def compress_lz4block(src, block_size: int = 1 << 16) -> bytes:
     return out[:r].tobytes()
 
 
-def decompress_lz4block(src, max_decoded: int) -> bytes:
+def decompress_lz4block(src, max_decoded: int, stop_on_empty_block: bool = True) -> bytes:
+    """LZ4BlockInputStream(in, stopOnEmptyBlock) read to its end (LZ4BlockInputStream.java:60-72, default true :100-104)."""
     s = _view(src)
     out = np.empty(max(max_decoded, 1), dtype=np.uint8)
-    r = N.lib().b200lz4block_decompress_host(s.ctypes.data, len(s), out.ctypes.data, max_decoded)
+    r = N.lib().b200lz4block_decompress_host(s.ctypes.data, len(s), out.ctypes.data, max_decoded, int(bool(stop_on_empty_block)), None)
     N.check(r)
     if r == -1:
         raise EOFError("Stream ended prematurely")                           # LZ4BlockInputStream.java:197

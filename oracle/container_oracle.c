@@ -47,12 +47,13 @@ int64_t orc_lz4block_compress(const uint8_t* src, size_t n, uint8_t* dst, int bs
     return (int64_t)(o + HDR);
 }
 
-int64_t orc_lz4block_decompress(const uint8_t* src, size_t n, uint8_t* dst, size_t cap)
+/* stop: LZ4BlockInputStream's stopOnEmptyBlock (LZ4BlockInputStream.java:60-72,191-233) */
+int64_t orc_lz4block_decompress(const uint8_t* src, size_t n, uint8_t* dst, size_t cap, int stop)
 {
     size_t ip = 0, op = 0;
-    while (ip < n) {
+    for (;;) {
         int token, method, level; int32_t clen, olen; uint32_t check;
-        if (n - ip < HDR) return -1;
+        if (n - ip < HDR) { if (stop) return -1; break; }
         if (memcmp(src + ip, MAGIC, 8) != 0) return -2;
         token = src[ip + 8]; method = token & 0xF0; level = 10 + (token & 0x0F);
         if (method != 0x10 && method != 0x20) return -2;
@@ -60,7 +61,7 @@ int64_t orc_lz4block_decompress(const uint8_t* src, size_t n, uint8_t* dst, size
         if (olen > (1 << level) || olen < 0 || clen < 0 || (olen == 0 && clen != 0) || (olen != 0 && clen == 0) ||
             (method == 0x10 && olen != clen)) return -2;
         ip += HDR;
-        if (olen == 0) { if (check != 0) return -2; continue; }
+        if (olen == 0) { if (check != 0) return -2; if (stop) break; continue; }
         if (n - ip < (size_t)clen) return -1;
         if (cap - op < (size_t)olen) return -9;
         if (method == 0x10) memcpy(dst + op, src + ip, (size_t)olen);

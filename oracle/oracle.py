@@ -87,7 +87,7 @@ class Port(_Lib):
         L.orc_lz4block_compress.restype = C.c_int64
         L.orc_lz4block_compress.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_void_p]
         L.orc_lz4block_decompress.restype = C.c_int64
-        L.orc_lz4block_decompress.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
+        L.orc_lz4block_decompress.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int]
         L.orc_with_length_compress.restype = C.c_int
         L.orc_with_length_compress.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.orc_with_length_decompress.restype = C.c_int
@@ -192,10 +192,10 @@ class Port(_Lib):
         r = self.L.orc_lz4block_compress(_ptr(s), len(s), _ptr(d), block_size, _ptr(scratch))
         return d[:r].tobytes()
 
-    def lz4block_decompress(self, src, cap: int):
+    def lz4block_decompress(self, src, cap: int, stop_on_empty_block: bool = True):
         s = _as_u8(src)
         d = np.empty(max(cap, 1), dtype=np.uint8)
-        r = self.L.orc_lz4block_decompress(_ptr(s), len(s), _ptr(d), cap)
+        r = self.L.orc_lz4block_decompress(_ptr(s), len(s), _ptr(d), cap, int(stop_on_empty_block))
         return r, d[: max(r, 0)].tobytes()
 
     def with_length_compress(self, src) -> bytes:

@@ -50,10 +50,10 @@ cudaError_t launch_xxh64_long(const uint8_t* base, const uint64_t* off, const in
 { if (n) simt::launch((unsigned)n, 32, [&] { xxh64_long_kernel(base, off, len, seed, out, (uint32_t)n); }); return cudaSuccess; }
 cudaError_t launch_xxh32(const uint8_t* base, const uint64_t* off, const int32_t* len, uint32_t seed, uint32_t* out, size_t n, cudaStream_t st)
 { return launch_xxh32_long(base, off, len, seed, out, n, st); }
-cudaError_t launch_xxh32_frames_chained(const uint8_t* slots, const uint64_t* f_out_off, const uint32_t* f_first, const uint32_t* f_nblk, const uint32_t* f_bs,
+cudaError_t launch_xxh32_frames_chained(const uint8_t* slots, const uint64_t* blk_off, const uint32_t* f_first, const uint32_t* f_nblk,
                                         const int32_t* blk_comp, const int32_t* blk_rawlen, const int32_t* c_res, uint32_t* out, size_t n, cudaStream_t)
 {   // (the emulator runs launches one after the other: the decoder has finished, nothing spins)
-    if (n) simt::launch((unsigned)n, 32, [&] { xxh32_frames_chained_kernel(slots, f_out_off, f_first, f_nblk, f_bs, blk_comp, blk_rawlen, c_res, out, (uint32_t)n); });
+    if (n) simt::launch((unsigned)n, 32, [&] { xxh32_frames_chained_kernel(slots, blk_off, f_first, f_nblk, blk_comp, blk_rawlen, c_res, out, (uint32_t)n); });
     return cudaSuccess;
 }
 cudaError_t launch_xxh64(const uint8_t* base, const uint64_t* off, const int32_t* len, uint64_t seed, uint64_t* out, size_t n, cudaStream_t st)

@@ -576,6 +576,73 @@ def test_frame_batch_decoder(b200, port):
     assert e.value.code == -9
 
 
+def _frame_of_pieces(port, pieces, bs_code, content_checksum=True, block_checksum=False, stored=()):
+    """an LZ4 frame whose blocks are exactly `pieces` (what LZ4FrameOutputStream writes when flush() is called between
+    writes, LZ4FrameOutputStream.java:204-251,268-277): short blocks anywhere, stored when they do not shrink or when asked"""
+    hdr = bytes([0x60 | (0x10 if block_checksum else 0) | (0x04 if content_checksum else 0), bs_code << 4])
+    out = bytearray(b"\x04\x22\x4d\x18" + hdr + bytes([(port.xxh32(hdr, 0) >> 8) & 0xFF]))
+    for i, piece in enumerate(pieces):
+        c = port.compress(piece)
+        raw = i in stored or len(c) >= len(piece)
+        payload = piece if raw else c
+        out += (len(payload) | (0x80000000 if raw else 0)).to_bytes(4, "little") + payload
+        if block_checksum:
+            out += port.xxh32(payload, 0).to_bytes(4, "little")
+    out += (0).to_bytes(4, "little")
+    if content_checksum:
+        out += port.xxh32(b"".join(pieces), 0).to_bytes(4, "little")
+    return bytes(out)
+
+
+def test_frames_written_with_flush(b200, port):
+    """short blocks before the last one: the content checksum is folded across block boundaries that are not multiples
+    of 16 on the device, the blocks are packed on the device, and a stream of tiny blocks asks for slots of its own size
+    (not blockMaxSize each).  Against the restated reader (LZ4FrameInputStream.java:258-321)."""
+    rng = random.Random(77)
+    base = port.datagen(1 << 20, 0.5, 0.0, 9).tobytes()
+    for trial in range(12):
+        bs_code = rng.choice((4, 5, 6, 7))
+        bs = 1 << (8 + 2 * bs_code)
+        sizes = [rng.choice((1, 3, 5, 15, 16, 17, 31, 100, 4097, 65535, min(bs, 65536), min(bs, 200000))) for _ in range(rng.randrange(1, 40))]
+        if trial == 0:
+            sizes = [5] * 300                                     # nothing but 5-byte stored blocks
+        if trial == 1:
+            sizes = [bs, 7, bs, bs, 1, 16, 33]
+        pieces = []
+        for n in sizes:
+            o = rng.randrange(0, len(base) - n) if n < len(base) else 0
+            pieces.append(rng.randbytes(n) if rng.random() < 0.2 else (base * (n // len(base) + 1))[o:o + n])
+        stored = {i for i in range(len(pieces)) if rng.random() < 0.15}
+        f = _frame_of_pieces(port, pieces, bs_code, content_checksum=trial % 3 != 2, block_checksum=bool(trial & 1), stored=stored)
+        want = b"".join(pieces)
+        r, out = port.frame_decompress(f, len(want) + 8)
+        assert r == len(want) and out == want, trial                # the builder writes what the restated reader accepts
+        assert b200.decompress_frames(f, len(want) + 8) == want, (trial, sizes)
+        both = f + port.frame_compress(base[:70000], 4, 1) + f       # gapped and contiguous frames in one call
+        assert b200.decompress_frames(both, 2 * len(want) + 70000) == want + base[:70000] + want, trial
+        if trial % 3 != 2 and want:
+            bad = bytearray(f); bad[-1] ^= 0x40                      # content checksum of a gapped frame
+            with pytest.raises(b200.LZ4FrameError) as e:
+                b200.decompress_frames(bytes(bad), len(want) + 8)
+            assert e.value.code == -7, trial
+        if want:
+            with pytest.raises(b200.LZ4FrameError) as e:
+                b200.decompress_frames(f, len(want) - 1)
+            assert e.value.code == -9
+    # slots: 300 five-byte stored blocks in a 4 MiB-block frame need kilobytes, not 300 x 4 MiB
+    import ctypes
+    from importlib import import_module
+    N = import_module(b200.__name__ + "._native")
+    f = np.frombuffer(_frame_of_pieces(port, [b"12345"] * 300, 7, stored=set(range(300))), dtype=np.uint8)
+    slot, err = ctypes.c_uint64(0), ctypes.c_int(0)
+    ix = N.lib().b200lz4f_index_create(f.ctypes.data, len(f), ctypes.byref(slot), ctypes.byref(err))
+    assert ix and err.value == 0 and slot.value == 300 * 16, (err.value, slot.value)
+    offs = np.zeros(300, dtype=np.uint64)
+    N.lib().b200lz4f_index_block_offsets(ix, offs.ctypes.data)
+    assert (offs == np.arange(300, dtype=np.uint64) * 16).all()
+    N.lib().b200lz4f_index_free(ix)
+
+
 def test_frame_writer_and_lz4java_containers(b200, port):
     """(f)-2..4: frames / LZ4Block streams / length-prefixed blocks WRITTEN on the GPU path are read by the CPU
     restatements (and by the reference's LZ4F_decompress when available), and vice versa"""
@@ -600,7 +667,12 @@ def test_frame_writer_and_lz4java_containers(b200, port):
             r, out = port.lz4block_decompress(blob, n)
             assert r == n and out == data, (n, blk)
             assert b200.decompress_lz4block(port.lz4block_compress(data, blk), n) == data
-            assert b200.decompress_lz4block(blob + blob, 2 * n) == data + data
+            assert b200.decompress_lz4block(blob + blob, 2 * n, stop_on_empty_block=False) == data + data
+            assert b200.decompress_lz4block(blob + blob, 2 * n) == data                     # stopOnEmptyBlock, the reference's default
+            assert b200.decompress_lz4block(blob + b"not a block", n) == data
+            assert b200.decompress_lz4block(blob[:-21] + b"LZ4", n, stop_on_empty_block=False) == data
+            with pytest.raises(EOFError):
+                b200.decompress_lz4block(blob[:-21], n)                                      # no end block (LZ4BlockInputStream.java:192-198)
         wl = b200.compress_with_length(data)
         assert port.with_length_decompress(wl, n) == (len(wl), data)
         assert b200.decompress_with_length(port.with_length_compress(data)) == data

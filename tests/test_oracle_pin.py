@@ -131,8 +131,12 @@ def test_container_restatements_roundtrip(port):
             assert blob[:8] == b"LZ4Block" and blob[-21:-13] == b"LZ4Block"
             r, out = port.lz4block_decompress(blob, n)
             assert r == n and out == data, (n, bs)
-            r, out = port.lz4block_decompress(blob + blob, 2 * n)              # concatenated streams (LZ4BlockStreamingTest.java:309-348)
+            r, out = port.lz4block_decompress(blob + blob, 2 * n, False)       # concatenated streams (LZ4BlockStreamingTest.java:309-348)
             assert r == 2 * n and out == data + data
+            r, out = port.lz4block_decompress(blob + b"trailing bytes", n)     # stopOnEmptyBlock (the default): the rest is not read
+            assert r == n and out == data
+            assert port.lz4block_decompress(blob[:-21], n)[0] == -1            # no end block: "Stream ended prematurely" (:192-198)
+            assert port.lz4block_decompress(blob[:-21] + b"LZ4", n, False) == (n, data)   # ... quiet end when not stopping (:193-194)
         wl = port.with_length_compress(data)
         assert int.from_bytes(wl[:4], "little") == n
         r, out = port.with_length_decompress(wl, n)
