@@ -114,6 +114,21 @@ int b200xxh32_batch_dev(const uint8_t* base, const uint64_t* off, const int32_t*
 int b200xxh64_batch_dev(const uint8_t* base, const uint64_t* off, const int32_t* len,
                         uint64_t seed, uint64_t* out, size_t n, void* stream);
 
+/* Packing on the device -- what *_compact_host does before its copy back, for callers whose blocks stay in HBM: block i's
+ * lens[i] bytes (<= 0 counts as none) move from slots + slot_off[i] to out + out_off[i]; out_off[] = the exclusive prefix
+ * sums of lens[], *total = their sum (device pointers all; out needs sum(lens) bytes).  Asynchronous on `stream`. */
+int b200lz4_compact_dev(const uint8_t* slots, const uint64_t* slot_off, const int32_t* lens, uint8_t* out, uint64_t* out_off,
+                        uint64_t* total, size_t n, void* stream);
+/* Device-side stitch of per-GPU packed shards into one stream: shard g is shard_total[g] packed bytes
+ * at shard_ptr[g] in the memory of device shard_dev[g] (a HOST array of device pointers; totals on the host -- 8 bytes per
+ * GPU, the only thing exchanged).  Shard g lands in dst (memory of device dst_dev, dst_capacity bytes) at the sum of the totals
+ * before it, reported in shard_pos[g] (host, may be NULL): one peer copy per shard, each on a stream of its source device, all
+ * in flight together (NVLink between peers, otherwise staged by the driver).  A block at out_off[i] inside shard g is at
+ * shard_pos[g] + out_off[i] in dst.  The shards must be complete before the call (synchronise their producers); returns when
+ * every copy has landed.  Needs no worker threads and no host buffer; the caller's current device is left as it was. */
+int b200lz4_stitch_shards_dev(const void* const* shard_ptr, const int* shard_dev, const uint64_t* shard_total, int nshard,
+                              void* dst, int dst_dev, size_t dst_capacity, uint64_t* shard_pos);
+
 /* ---------------------------------------------------------------- batches, HOST buffers
  * Same contracts, but every pointer is a HOST pointer.  The library chunks the batch and
  * pipelines H2D copy / kernel / D2H copy on several streams of the current device.  Blocks

@@ -47,6 +47,8 @@ SYMBOLS = [
     ("b200lz4_decompress_fast_batch_dev", _i, _BATCH + [_vp]),
     ("b200xxh32_batch_dev", _i, [_vp, _vp, _vp, _u32, _vp, _sz, _vp]),
     ("b200xxh64_batch_dev", _i, [_vp, _vp, _vp, _u64, _vp, _sz, _vp]),
+    ("b200lz4_compact_dev", _i, [_vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    ("b200lz4_stitch_shards_dev", _i, [_vp, _vp, _vp, _i, _vp, _i, _sz, _vp]),
     ("b200lz4_compress_fast_batch_host", _i, _BATCH + [_i]),
     ("b200lz4_compress_hc_batch_host", _i, _BATCH + [_i]),
     ("b200lz4_decompress_safe_batch_host", _i, _BATCH),

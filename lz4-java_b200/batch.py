@@ -202,3 +202,29 @@ def xxh64_batch_dev(buf, off, length, out, seed=0):
     N.check(N.lib().b200xxh64_batch_dev(buf.data_ptr(), off.data_ptr(), length.data_ptr(), seed & 0xFFFFFFFFFFFFFFFF,
                                         out.data_ptr(), off.numel(), _stream_ptr()))
     return out
+
+
+def compact_dev(slots, slot_off, lens, out, out_off, total):
+    """device-resident packing (b200lz4_compact_dev): out_off <- exclusive prefix sums of lens, total[0] <- their sum,
+    block i's bytes move from slots + slot_off[i] to out + out_off[i].  Torch CUDA tensors, torch's current stream."""
+    N.check(N.lib().b200lz4_compact_dev(slots.data_ptr(), slot_off.data_ptr(), lens.data_ptr(), out.data_ptr(), out_off.data_ptr(),
+                                        total.data_ptr(), slot_off.numel(), _stream_ptr()))
+    return out_off, total
+
+
+def stitch_shards_dev(shards, totals, dst):
+    """one process, several GPUs: packed shard g (a uint8 CUDA tensor on its own GPU, totals[g] bytes of it) lands in `dst`
+    (a uint8 CUDA tensor on any GPU) at the sum of the totals before it -- peer copies, b200lz4_stitch_shards_dev.
+    -> positions of the shards in dst (uint64)"""
+    import ctypes
+    import torch
+    k = len(shards)
+    for t in shards:
+        torch.cuda.synchronize(t.device)                          # the shards must be complete (see the header)
+    ptrs = (ctypes.c_void_p * k)(*[int(t.data_ptr()) for t in shards])
+    devs = (ctypes.c_int * k)(*[int(t.device.index or 0) for t in shards])
+    tot = np.asarray([int(x) for x in totals], dtype=np.uint64)
+    pos = np.zeros(k, dtype=np.uint64)
+    N.check(N.lib().b200lz4_stitch_shards_dev(ptrs, devs, _p(tot), k, dst.data_ptr(), int(dst.device.index or 0), dst.numel(), _p(pos)))
+    return pos
+

@@ -697,6 +697,69 @@ int b200xxh64_batch_dev(const uint8_t* base, const uint64_t* off, const int32_t*
     return 0;
 }
 
+// ---- device-resident packing and the cross-GPU stitch (SURVEY.md 8e "optional next", (f)-4)
+int b200lz4_compact_dev(const uint8_t* slots, const uint64_t* slot_off, const int32_t* lens, uint8_t* out, uint64_t* out_off,
+                        uint64_t* total, size_t n, void* stream)
+{
+    int rc = ensure_device(); if (rc) return rc;
+    if (n > 0xFFFFFFFFull) return fail_arg("n");
+    if (!total || (n && (!slots || !slot_off || !lens || !out || !out_off))) return fail_arg("null pointer");
+    if (n == 0) { CK(cudaMemsetAsync(total, 0, sizeof(uint64_t), (cudaStream_t)stream)); return 0; }
+    g_launches.fetch_add(2, std::memory_order_relaxed);
+    CK(launch_compact(slots, slot_off, lens, out, out_off, total, n, (cudaStream_t)stream));
+    return 0;
+}
+
+int b200lz4_stitch_shards_dev(const void* const* shard_ptr, const int* shard_dev, const uint64_t* shard_total, int nshard,
+                              void* dst, int dst_dev, size_t dst_capacity, uint64_t* shard_pos)
+{
+    if (nshard < 1 || nshard > 64) return fail_arg("nshard must be 1..64");
+    if (!shard_ptr || !shard_dev || !shard_total || !dst) return fail_arg("null pointer");
+    int cnt = b200lz4_device_count();
+    if (cnt < 0) return cnt;
+    if (dst_dev < 0 || dst_dev >= cnt) return fail_arg("dst_dev");
+    uint64_t acc = 0;
+    std::vector<uint64_t> pos((size_t)nshard);
+    for (int g = 0; g < nshard; g++) {
+        if (shard_dev[g] < 0 || shard_dev[g] >= cnt) return fail_arg("device index in shard_dev[]");
+        if (shard_total[g] && !shard_ptr[g]) return fail_arg("null shard");
+        pos[(size_t)g] = acc; acc += shard_total[g];
+        if (shard_pos) shard_pos[g] = pos[(size_t)g];
+    }
+    if (acc > dst_capacity) return fail_arg("dst_capacity must hold the sum of shard_total[]");
+    int my_cuda_device = -1;
+    if (cudaGetDevice(&my_cuda_device) != cudaSuccess) my_cuda_device = -1;
+    // one copy per shard, each on a stream of its SOURCE device, so the links into dst_dev are all busy at once
+    std::vector<cudaStream_t> st((size_t)nshard, nullptr);
+    cudaError_t err = cudaSuccess; const char* where = "";
+    for (int g = 0; g < nshard && err == cudaSuccess; g++) {
+        if (!shard_total[g]) continue;
+        if ((err = cudaSetDevice(shard_dev[g])) != cudaSuccess) { where = "cudaSetDevice"; break; }
+        if (shard_dev[g] != dst_dev) {
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, shard_dev[g], dst_dev) == cudaSuccess && can) {
+                const cudaError_t e = cudaDeviceEnablePeerAccess(dst_dev, 0);        // direct NVLink/PCIe stores; without it the copy is staged
+                if (e != cudaSuccess) (void)cudaGetLastError();                      // (already enabled, or not possible: either way the copy below works)
+            }
+        }
+        if ((err = cudaStreamCreateWithFlags(&st[(size_t)g], cudaStreamNonBlocking)) != cudaSuccess) { st[(size_t)g] = nullptr; where = "cudaStreamCreate"; break; }
+        uint8_t* to = (uint8_t*)dst + pos[(size_t)g];
+        err = shard_dev[g] == dst_dev ? cudaMemcpyAsync(to, shard_ptr[g], shard_total[g], cudaMemcpyDeviceToDevice, st[(size_t)g])
+                                      : cudaMemcpyPeerAsync(to, dst_dev, shard_ptr[g], shard_dev[g], shard_total[g], st[(size_t)g]);
+        where = "peer copy";
+    }
+    for (int g = 0; g < nshard; g++) {
+        if (!st[(size_t)g]) continue;
+        cudaSetDevice(shard_dev[g]);
+        const cudaError_t e = cudaStreamSynchronize(st[(size_t)g]);
+        if (err == cudaSuccess && e != cudaSuccess) { err = e; where = "cudaStreamSynchronize"; }
+        cudaStreamDestroy(st[(size_t)g]);
+    }
+    if (my_cuda_device >= 0) cudaSetDevice(my_cuda_device);
+    if (err != cudaSuccess) return fail_cuda(err, where);
+    return 0;
+}
+
 // ---- host-buffer batches
 int b200lz4_compress_fast_batch_host(const uint8_t* src_base, const uint64_t* src_off, const int32_t* src_len,
                                      uint8_t* dst_base, const uint64_t* dst_off, const int32_t* dst_cap,

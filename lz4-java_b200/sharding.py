@@ -28,6 +28,40 @@ def packed_offsets(local_total: int, group=None) -> tuple[int, int]:
     return sum(totals[:rank]), sum(totals)
 
 
+def stitch_packed(packed, local_total: int, dst_rank: int = 0, group=None):
+    """One process per GPU: every rank holds its packed shard (`packed[:local_total]`, a uint8 tensor on its GPU); rank
+    `dst_rank` gets the shards of all ranks back to back, in rank order, in one tensor on ITS GPU -- the device-side
+    counterpart of the gather-write a host caller does with `*_compact_host_multi`'s pieces.
+    Exchange: one all_gather of an int64 per rank (`packed_offsets`), then one point-to-point transfer per rank straight
+    into the destination tensor at the computed offset (NCCL send/recv: GPU-to-GPU over NVLink, no host copy; gloo on CPU
+    tensors in the tests).  -> (stitched tensor or None on the other ranks, this rank's offset, grand total)"""
+    import torch
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    mine = torch.tensor([local_total], dtype=torch.int64, device=dev)
+    alls = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(alls, mine, group=group)
+    totals = [int(t.item()) for t in alls]
+    offs = [sum(totals[:r]) for r in range(world)]
+    out = None
+    ops = []
+    if rank == dst_rank:
+        out = torch.empty(max(sum(totals), 1), dtype=torch.uint8, device=packed.device)
+        out[offs[rank]:offs[rank] + totals[rank]].copy_(packed[:totals[rank]])
+        for r in range(world):
+            if r != rank and totals[r]:
+                ops.append(dist.P2POp(dist.irecv, out[offs[r]:offs[r] + totals[r]], r, group))
+    elif local_total:
+        ops.append(dist.P2POp(dist.isend, packed[:local_total].contiguous(), dst_rank, group))
+    if ops:
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+    if out is not None:
+        out = out[:sum(totals)]
+    return out, offs[rank], sum(totals)
+
+
 def max_over_ranks(seconds: float, group=None) -> float:
     """device-time aggregation rule of the bench contract: a multi-GPU step takes as long as its slowest rank"""
     import torch

@@ -62,6 +62,9 @@ inline int& current_device() { static thread_local int d = 0; return d; }
 }
 static inline cudaError_t cudaGetDeviceCount(int* n) { *n = simt_rt::device_count(); return cudaSuccess; }
 static inline cudaError_t cudaSetDevice(int d) { if (d < 0 || d >= simt_rt::device_count()) return 101; simt_rt::current_device() = d; return cudaSuccess; }
+static inline cudaError_t cudaDeviceCanAccessPeer(int* can, int a, int b) { *can = a != b; return cudaSuccess; }
+static inline cudaError_t cudaDeviceEnablePeerAccess(int, unsigned) { return cudaSuccess; }
+static inline cudaError_t cudaMemcpyPeerAsync(void* d, int, const void* s, int, size_t n, cudaStream_t = nullptr) { if (n) std::memmove(d, s, n); return cudaSuccess; }
 static inline cudaError_t cudaGetDevice(int* d) { *d = simt_rt::current_device(); return cudaSuccess; }
 static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, unsigned) { *s = std::malloc(8); return cudaSuccess; }
 static inline cudaError_t cudaStreamDestroy(cudaStream_t s) { std::free(s); return cudaSuccess; }

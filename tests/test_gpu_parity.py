@@ -1180,3 +1180,87 @@ def test_error_offsets_beyond_a_million_are_decoder_errors(b200, checker):
     with pytest.raises(b200.LZ4Exception) as e:
         b200.LZ4Factory.b200Instance().safeDecompressor().decompress(bytes(c), 0, len(c), bytearray(len(d)), 0, len(d))
     assert "offset" in str(e.value)
+
+
+class _DevMem:
+    """device buffers for tests that call the C ABI with raw device pointers: torch CUDA tensors on a GPU box, plain
+    numpy arrays under the emulator build (its "device memory" is the host heap)"""
+
+    def __init__(self):
+        self.sim = "sim" in os.environ.get("B200LZ4_TEST_SO", "")
+        if not self.sim:
+            import torch
+            self.torch = torch
+
+    def up(self, arr, device=0):
+        arr = np.ascontiguousarray(arr)
+        if self.sim:
+            return arr.copy()
+        return self.torch.from_numpy(arr.view(np.uint8).reshape(-1)).to(self.torch.device("cuda", device))
+
+    def zeros(self, nbytes, device=0):
+        return self.up(np.zeros(max(nbytes, 16), dtype=np.uint8), device)
+
+    def ptr(self, buf):
+        return buf.ctypes.data if self.sim else buf.data_ptr()
+
+    def down(self, buf, dtype=np.uint8):
+        if not self.sim:
+            self.torch.cuda.synchronize()
+            buf = buf.cpu().numpy()
+        return buf.view(np.uint8).reshape(-1).view(dtype)
+
+
+def test_device_side_compaction_and_stitch(b200, checker):
+    """(f)-4 with everything in HBM: each shard's blocks are compressed into bound-sized slots, packed on the device
+    (b200lz4_compact_dev) and the packed shards are stitched into one stream by peer copies at offsets computed from the
+    shard totals (b200lz4_stitch_shards_dev).  The stitched stream must be byte-identical to what one GPU packs for the whole
+    batch (b200lz4_compress_fast_compact_host), block offsets included.  A one-GPU box lists device 0 for every shard
+    (device-to-device copies); the emulator build pretends SIMT_DEVICES GPUs; a multi-GPU box uses them all."""
+    import ctypes
+    L = b200._native.lib()
+    M = _DevMem()
+    ndev = L.b200lz4_device_count()
+    assert ndev >= 1
+    datas = [checker.datagen(n, 0.5, 0.0, s).tobytes() for s, n in enumerate([65536, 1, 0, 40000, 65536, 13, 70000, 5000, 65536, 300, 12, 65536, 100000])]
+    src, soff, slen = corpus.pack(datas)
+    want = np.zeros(sum(b200.max_compressed_length(len(d)) + 16 for d in datas), dtype=np.uint8)
+    w_off, w_len, w_total = b200.batch.compress_fast_compact_host(src, soff, slen, want)
+    for shard_devs in ([0], [0, 0, 0], [g % ndev for g in range(5)], list(range(ndev))[::-1]):
+        k = len(shard_devs)
+        bufs, totals, offs_all = [], [], []
+        for g, dv in enumerate(shard_devs):
+            lo, hi = len(datas) * g // k, len(datas) * (g + 1) // k
+            assert L.b200lz4_set_device(dv) == 0
+            if not M.sim:
+                M.torch.cuda.set_device(dv)
+            n = hi - lo
+            coff, ccap, ctotal = _slots([b200.max_compressed_length(len(d)) for d in datas[lo:hi]])
+            d_src, d_soff, d_slen = M.up(src, dv), M.up(soff[lo:hi], dv), M.up(slen[lo:hi], dv)
+            d_coff, d_ccap = M.up(coff, dv), M.up(ccap, dv)
+            d_slots, d_clen = M.zeros(ctotal, dv), M.zeros(4 * n, dv)
+            d_pack, d_poff, d_tot = M.zeros(ctotal, dv), M.zeros(8 * n, dv), M.zeros(8, dv)
+            if n:
+                assert L.b200lz4_compress_fast_batch_dev(M.ptr(d_src), M.ptr(d_soff), M.ptr(d_slen), M.ptr(d_slots), M.ptr(d_coff), M.ptr(d_ccap),
+                                                         M.ptr(d_clen), n, 0, None) == 0
+            assert L.b200lz4_compact_dev(M.ptr(d_slots), M.ptr(d_coff), M.ptr(d_clen), M.ptr(d_pack), M.ptr(d_poff), M.ptr(d_tot), n, None) == 0
+            tot = int(M.down(d_tot, np.uint64)[0])
+            clen = M.down(d_clen, np.int32)[:n]
+            assert (clen == w_len[lo:hi]).all() and tot == int(clen.sum()), (shard_devs, g)
+            bufs.append(d_pack); totals.append(tot); offs_all.append(M.down(d_poff, np.uint64)[:n].copy())
+        dst_dev = shard_devs[-1]
+        d_out = M.zeros(sum(totals) + 32, dst_dev)
+        ptrs = (ctypes.c_void_p * k)(*[M.ptr(b) for b in bufs])
+        devs = (ctypes.c_int * k)(*shard_devs)
+        tot = np.asarray(totals, dtype=np.uint64); pos = np.zeros(k, dtype=np.uint64)
+        assert L.b200lz4_stitch_shards_dev(ptrs, devs, tot.ctypes.data, k, M.ptr(d_out), dst_dev, sum(totals) + 32, pos.ctypes.data) == 0
+        got = M.down(d_out)
+        assert sum(totals) == w_total and got[:w_total].tobytes() == want[:w_total].tobytes(), shard_devs
+        assert (got[w_total:w_total + 32] == 0).all()
+        where = np.concatenate([o + p for o, p in zip(offs_all, pos)])
+        assert (where == w_off).all(), shard_devs
+        # too small a destination is refused before anything is copied
+        assert L.b200lz4_stitch_shards_dev(ptrs, devs, tot.ctypes.data, k, M.ptr(d_out), dst_dev, sum(totals) - 1, None) == b200._native.E_ARG
+    assert L.b200lz4_set_device(0) == 0
+    if not M.sim:
+        M.torch.cuda.set_device(0)
