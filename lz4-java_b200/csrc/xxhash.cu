@@ -229,7 +229,19 @@ __device__ __forceinline__ uint32_t xxh32_chain_init(uint32_t seed, int lane)
     return c == 0 ? seed + P32_1 + P32_2 : c == 1 ? seed + P32_2 : c == 2 ? seed : seed - P32_1;
 }
 
-// Consume `rows` rows of 128 bytes starting at p (any alignment) into this lane's chain.
+// Consume `rows` rows of 128 bytes starting at p (any alignment) into this lane's chain.  CG: the bytes are being produced by
+// ANOTHER kernel while this one runs (the frame variant below) -- every load then goes to L2 (ld.global.cg); a line this SM's
+// L1 took earlier may predate a neighbouring block's bytes.
+template <bool CG>
+__device__ __forceinline__ uint32_t xxh_ldw(const uint32_t* p)
+{
+#ifndef B200_HOST_SIM
+    if constexpr (CG) return __ldcg(p);
+#endif
+    return *p;
+}
+
+template <bool CG = false>
 __device__ __forceinline__ uint32_t xxh32_warp_rows(uint32_t v, const uint8_t* __restrict__ p, size_t rows, int lane)
 {
     constexpr int R = 8;
@@ -239,8 +251,8 @@ __device__ __forceinline__ uint32_t xxh32_warp_rows(uint32_t v, const uint8_t* _
     const int c = lane & 3;
     auto ldrow = [&](size_t r) -> uint32_t {
         const size_t i = r * 32 + lane;
-        const uint32_t a = W[i];
-        return sh ? __funnelshift_r(a, W[i + 1], sh) : a;
+        const uint32_t a = xxh_ldw<CG>(W + i);
+        return sh ? __funnelshift_r(a, xxh_ldw<CG>(W + i + 1), sh) : a;
     };
     uint32_t cur[R], nxt[R];
     const size_t groups = rows / R;
@@ -270,11 +282,23 @@ __device__ __forceinline__ uint32_t xxh32_warp_rows(uint32_t v, const uint8_t* _
 }
 
 // All stripes of [p, p + 16*stripes): rows by the warp, the last < 8 stripes by direct loads.
+template <bool CG = false>
 __device__ __forceinline__ uint32_t xxh32_warp_stripes(uint32_t v, const uint8_t* __restrict__ p, size_t stripes, int lane)
 {
     const size_t rows = stripes >> 3;
-    v = xxh32_warp_rows(v, p, rows, lane);
-    for (size_t t = rows << 3; t < stripes; t++) v = round32(v, load_u32_unaligned(p + 16 * t + 4 * (lane & 3)));
+    v = xxh32_warp_rows<CG>(v, p, rows, lane);
+    for (size_t t = rows << 3; t < stripes; t++) {
+        const uint8_t* q = p + 16 * t + 4 * (lane & 3);
+        if constexpr (CG) {
+            const uintptr_t a = reinterpret_cast<uintptr_t>(q);
+            const uint32_t* w = reinterpret_cast<const uint32_t*>(a & ~uintptr_t(3));
+            const uint32_t sh = (uint32_t(a) & 3u) * 8u;
+            const uint32_t lo = xxh_ldw<true>(w);
+            v = round32(v, sh ? __funnelshift_r(lo, xxh_ldw<true>(w + 1), sh) : lo);
+        } else {
+            v = round32(v, load_u32_unaligned(q));
+        }
+    }
     return v;
 }
 
@@ -319,7 +343,18 @@ cudaError_t launch_xxh32_long(const uint8_t* base, const uint64_t* off, const in
 //   blk_off[b]: where block b lies in the slot layout;  blk_comp[b] >= 0: its index in the decoder's result array;  < 0: a
 //   stored block of blk_rawlen[b] bytes, already in place.  c_res[k] == FRAME_RES_PENDING until block k is decoded; a negative
 //   result ends the frame's hash (the host reports -6).  Blocks need not be full: the bytes of an unfinished 16-byte stripe
-//   wait in shared memory for the next block (a frame written with flush() calls has short blocks anywhere).
+//   wait in shared memory for the next block (a frame written with flush() calls has short blocks anywhere).  Short blocks
+//   share 32-byte sectors with their neighbours, which may be written after this warp looked at the sector: block bytes are
+//   read with ld.global.cg (L2), never through this SM's L1.
+__device__ __forceinline__ uint8_t ld_byte_l2(const uint8_t* p)
+{
+#ifndef B200_HOST_SIM
+    return __ldcg(p);
+#else
+    return *p;
+#endif
+}
+
 __global__ void __launch_bounds__(32)
 xxh32_frames_chained_kernel(const uint8_t* __restrict__ slots, const uint64_t* __restrict__ blk_off, const uint32_t* __restrict__ f_first,
                             const uint32_t* __restrict__ f_nblk, const int32_t* __restrict__ blk_comp, const int32_t* __restrict__ blk_rawlen,
@@ -350,7 +385,7 @@ xxh32_frames_chained_kernel(const uint8_t* __restrict__ slots, const uint64_t* _
         total += len;
         if (carry) {                                        // finish the stripe the previous block left open
             const uint32_t t = min(16u - carry, len);
-            if (uint32_t(lane) < t) s_carry[carry + lane] = p[lane];
+            if (uint32_t(lane) < t) s_carry[carry + lane] = ld_byte_l2(p + lane);
             __syncwarp();
             carry += t; p += t; len -= t;
             if (carry < 16u) continue;
@@ -358,9 +393,9 @@ xxh32_frames_chained_kernel(const uint8_t* __restrict__ slots, const uint64_t* _
             __syncwarp();
         }
         const size_t stripes = size_t(len) >> 4;
-        if (stripes) { v = xxh32_warp_stripes(v, p, stripes, lane); big = true; }
+        if (stripes) { v = xxh32_warp_stripes<true>(v, p, stripes, lane); big = true; }
         carry = len & 15u;
-        if (uint32_t(lane) < carry) s_carry[lane] = p[16 * stripes + lane];
+        if (uint32_t(lane) < carry) s_carry[lane] = ld_byte_l2(p + 16 * stripes + lane);
         __syncwarp();
     }
     const uint32_t h = big ? xxh32_chain_merge(v) : 0u + P32_5;
