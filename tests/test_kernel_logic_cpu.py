@@ -344,13 +344,13 @@ def test_host_layer_on_the_emulator_library():
     unchanged over a stand-in CUDA runtime); a few of the GPU parity tests then run against it in a subprocess (the
     product loader of this process is left alone): the batch pipeline with bounce buffers and compaction, the
     single-block factory API with its exception contract, streaming hashes, the drain of a pipeline call that
-    fails half way, the JNI shim, and the range-sharded multi-GPU calls over three pretend devices (SIMT_DEVICES).  The full file takes ~20 minutes this way
+    fails half way, the JNI shim, the range-sharded multi-GPU calls and the device-side stitch over three pretend devices (SIMT_DEVICES), frames written with flush().  The full file takes ~20 minutes this way
     (see tests/simt/README.md); this is the one-minute slice."""
     import sys
     subprocess.run(["bash", os.path.join(HERE, "simt", "build_sim_library.sh")], check=True, capture_output=True)
     # 1 MiB pipeline chunks: the 40-block batches of these tests then cross chunk boundaries (all three stream slots in use)
     env = dict(os.environ, B200LZ4_TEST_SO=os.path.join(HERE, "simt", "_build", "libb200lz4_sim.so"), B200LZ4_CHUNK_MB="1", SIMT_DEVICES="3")
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(HERE, "test_gpu_parity.py"), "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider",
-                        "-W", "ignore::DeprecationWarning", "-k", "factory_api or compact_host or xxhash_streaming or self_roundtrip or failed_pipeline or contexts_are_reused or jni_shim or multi_gpu_range"],
+                        "-W", "ignore::DeprecationWarning", "-k", "factory_api or compact_host or xxhash_streaming or self_roundtrip or failed_pipeline or contexts_are_reused or jni_shim or multi_gpu_range or written_with_flush or device_side_compaction"],
                        env=env, cwd=ROOT, capture_output=True, text=True)
-    assert r.returncode == 0 and "8 passed" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.returncode == 0 and "10 passed" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
