@@ -576,6 +576,35 @@ def test_frame_batch_decoder(b200, port):
     assert e.value.code == -9
 
 
+class _DevMem:
+    """device buffers for tests that call the C ABI with raw device pointers: torch CUDA tensors on a GPU box, plain
+    numpy arrays under the emulator build (its "device memory" is the host heap)"""
+
+    def __init__(self):
+        self.sim = "sim" in os.environ.get("B200LZ4_TEST_SO", "")
+        if not self.sim:
+            import torch
+            self.torch = torch
+
+    def up(self, arr, device=0):
+        arr = np.ascontiguousarray(arr)
+        if self.sim:
+            return arr.copy()
+        return self.torch.from_numpy(arr.view(np.uint8).reshape(-1)).to(self.torch.device("cuda", device))
+
+    def zeros(self, nbytes, device=0):
+        return self.up(np.zeros(max(nbytes, 16), dtype=np.uint8), device)
+
+    def ptr(self, buf):
+        return buf.ctypes.data if self.sim else buf.data_ptr()
+
+    def down(self, buf, dtype=np.uint8):
+        if not self.sim:
+            self.torch.cuda.synchronize()
+            buf = buf.cpu().numpy()
+        return buf.view(np.uint8).reshape(-1).view(dtype)
+
+
 def _frame_of_pieces(port, pieces, bs_code, content_checksum=True, block_checksum=False, stored=()):
     """an LZ4 frame whose blocks are exactly `pieces` (what LZ4FrameOutputStream writes when flush() is called between
     writes, LZ4FrameOutputStream.java:204-251,268-277): short blocks anywhere, stored when they do not shrink or when asked"""
@@ -641,6 +670,30 @@ def test_frames_written_with_flush(b200, port):
     N.lib().b200lz4f_index_block_offsets(ix, offs.ctypes.data)
     assert (offs == np.arange(300, dtype=np.uint64) * 16).all()
     N.lib().b200lz4f_index_free(ix)
+    # the device entry point on a gapped frame: every check passes, -11 says "read the blocks one by one", and the blocks are
+    # where b200lz4f_index_block_offsets says, block_len_out bytes each
+    pieces = [base[:65536], base[100:107], base[7:65543], b"", base[5:38], rng.randbytes(300)]
+    pieces = [p for p in pieces if p]
+    f = np.frombuffer(_frame_of_pieces(port, pieces, 4, content_checksum=True, block_checksum=True), dtype=np.uint8)
+    M = _DevMem()
+    ix = N.lib().b200lz4f_index_create(f.ctypes.data, len(f), ctypes.byref(slot), ctypes.byref(err))
+    assert ix and err.value == 0
+    nb = N.lib().b200lz4f_index_blocks(ix)
+    assert nb == len(pieces) and N.lib().b200lz4f_index_frames(ix) == 1
+    d_src, d_slots = M.up(np.concatenate([f, np.zeros(64, dtype=np.uint8)])), M.zeros(slot.value + 64)
+    foff, flen, blen = np.zeros(1, dtype=np.uint64), np.zeros(1, dtype=np.uint64), np.zeros(nb, dtype=np.int32)
+    rc = N.lib().b200lz4f_decode_dev(ix, M.ptr(d_src), M.ptr(d_slots), foff.ctypes.data, flen.ctypes.data, blen.ctypes.data, None)
+    assert rc == -11 and int(flen[0]) == sum(map(len, pieces)) and [int(x) for x in blen] == [len(p) for p in pieces]
+    offs = np.zeros(nb, dtype=np.uint64)
+    N.lib().b200lz4f_index_block_offsets(ix, offs.ctypes.data)
+    got = M.down(d_slots)
+    for o, p in zip(offs, pieces):
+        assert got[int(o):int(o) + len(p)].tobytes() == p
+    bad = f.copy(); bad[-1] ^= 1                                   # the content checksum is verified BEFORE -11 is returned
+    ix2 = N.lib().b200lz4f_index_create(bad.ctypes.data, len(bad), ctypes.byref(slot), ctypes.byref(err))
+    d_bad = M.up(np.concatenate([bad, np.zeros(64, dtype=np.uint8)]))
+    assert N.lib().b200lz4f_decode_dev(ix2, M.ptr(d_bad), M.ptr(d_slots), None, None, None, None) == -7
+    N.lib().b200lz4f_index_free(ix); N.lib().b200lz4f_index_free(ix2)
 
 
 def test_frame_writer_and_lz4java_containers(b200, port):
@@ -1180,35 +1233,6 @@ def test_error_offsets_beyond_a_million_are_decoder_errors(b200, checker):
     with pytest.raises(b200.LZ4Exception) as e:
         b200.LZ4Factory.b200Instance().safeDecompressor().decompress(bytes(c), 0, len(c), bytearray(len(d)), 0, len(d))
     assert "offset" in str(e.value)
-
-
-class _DevMem:
-    """device buffers for tests that call the C ABI with raw device pointers: torch CUDA tensors on a GPU box, plain
-    numpy arrays under the emulator build (its "device memory" is the host heap)"""
-
-    def __init__(self):
-        self.sim = "sim" in os.environ.get("B200LZ4_TEST_SO", "")
-        if not self.sim:
-            import torch
-            self.torch = torch
-
-    def up(self, arr, device=0):
-        arr = np.ascontiguousarray(arr)
-        if self.sim:
-            return arr.copy()
-        return self.torch.from_numpy(arr.view(np.uint8).reshape(-1)).to(self.torch.device("cuda", device))
-
-    def zeros(self, nbytes, device=0):
-        return self.up(np.zeros(max(nbytes, 16), dtype=np.uint8), device)
-
-    def ptr(self, buf):
-        return buf.ctypes.data if self.sim else buf.data_ptr()
-
-    def down(self, buf, dtype=np.uint8):
-        if not self.sim:
-            self.torch.cuda.synchronize()
-            buf = buf.cpu().numpy()
-        return buf.view(np.uint8).reshape(-1).view(dtype)
 
 
 def test_device_side_compaction_and_stitch(b200, checker):
