@@ -204,6 +204,10 @@ int b200xxh64_batch_host_multi(const uint8_t* base, const uint64_t* off, const i
  * -9 dst too small, -10 unsupported descriptor, -11 (decode_dev only) every check passed but a frame has a short block
  * before its last one (flush()), so its content is not one run inside d_slots: read block b at block_off[b] for
  * block_len_out[b] bytes (b200lz4f_index_block_offsets).
+ * Errors come in STREAM order, as the reader would meet them: frame by frame the descriptor hash, block by block its checksum
+ * and its decode, at the EndMark content checksum then content size; a container that is cut short or malformed behind at
+ * least one frame header still gets an index, what precedes the bad spot is decoded and verified first, and decode_dev then
+ * returns the container's own code (-1, -2, -4, -10).
  * d_slots layout: a full block takes blockMaxSize bytes; a block that cannot fill it (a stored block, or a compressed one
  * of fewer than blockMaxSize/255 bytes) takes what it can decode to, rounded up to 16 -- slot_bytes does not grow with
  * blockMaxSize for a stream of tiny blocks. */

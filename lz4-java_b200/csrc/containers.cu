@@ -141,24 +141,27 @@ int64_t b200lz4block_decompress_host(const uint8_t* src, size_t n, uint8_t* dst,
     std::vector<uint64_t> soff, doff; std::vector<int32_t> savail, dlen, csz; std::vector<uint32_t> want;
     std::vector<uint64_t> hoff; std::vector<int32_t> hlen;
     size_t ip = 0, op = 0;
+    int64_t tail = 0;                    // what is wrong with the container itself, behind the blocks collected so far: the reader
+                                         // would have decoded and checked THOSE first, so their verdict comes first
     for (;;) {                                                                   // refill (:191-264)
-        if (n - ip < LZ4BLOCK_HEADER) { if (stopOnEmptyBlock) return -1; ip = n; break; }
-        if (memcmp(src + ip, LZ4BLOCK_MAGIC, 8) != 0) return -2;
+        if (n - ip < LZ4BLOCK_HEADER) { if (stopOnEmptyBlock) tail = -1; else ip = n; break; }
+        if (memcmp(src + ip, LZ4BLOCK_MAGIC, 8) != 0) { tail = -2; break; }
         const int token = src[ip + 8], method = token & 0xF0, level = 10 + (token & 0x0F);
-        if (method != METHOD_RAW && method != METHOD_LZ4) return -2;
+        if (method != METHOD_RAW && method != METHOD_LZ4) { tail = -2; break; }
         const int32_t clen = (int32_t)get32(src + ip + 9), olen = (int32_t)get32(src + ip + 13);
         const uint32_t check = get32(src + ip + 17);
         if (olen > (1 << level) || olen < 0 || clen < 0 || (olen == 0 && clen != 0) || (olen != 0 && clen == 0) ||
-            (method == METHOD_RAW && olen != clen)) return -2;
+            (method == METHOD_RAW && olen != clen)) { tail = -2; break; }
         ip += LZ4BLOCK_HEADER;
-        if (olen == 0) { if (check != 0) return -2; if (stopOnEmptyBlock) break; continue; }   // empty block (:225-233)
-        if (n - ip < (size_t)clen) return -1;
-        if (cap - op < (size_t)olen) return -9;
+        if (olen == 0) { if (check != 0) { tail = -2; break; } if (stopOnEmptyBlock) break; continue; }   // empty block (:225-233)
+        if (n - ip < (size_t)clen) { tail = -1; break; }
+        if (cap - op < (size_t)olen) { tail = -9; break; }
         if (method == METHOD_RAW) memcpy(dst + op, src + ip, (size_t)olen);
         else { soff.push_back(ip); savail.push_back(clen); doff.push_back(op); dlen.push_back(olen); csz.push_back(clen); }
         hoff.push_back(op); hlen.push_back(olen); want.push_back(check);
         ip += (size_t)clen; op += (size_t)olen;
     }
+    // per block the reader decodes, compares the consumed length, then the checksum -- all "Stream is corrupted" (:236-262)
     if (!soff.empty()) {
         std::vector<int32_t> res(soff.size());
         int rc = b200lz4_decompress_fast_batch_host(src, soff.data(), savail.data(), dst, doff.data(), dlen.data(), res.data(), soff.size());
@@ -171,6 +174,7 @@ int64_t b200lz4block_decompress_host(const uint8_t* src, size_t n, uint8_t* dst,
         if (rc) return rc;
         for (size_t i = 0; i < sums.size(); i++) if ((sums[i] & 0x0FFFFFFFu) != want[i]) return -2;
     }
+    if (tail) return tail;
     if (srcConsumed) *srcConsumed = ip;
     return (int64_t)op;
 }

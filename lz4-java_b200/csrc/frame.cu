@@ -32,6 +32,7 @@ struct FrameRec {
     size_t first_block, nblocks;
     uint32_t content_checksum; bool has_checksum;
     uint64_t out_off;                   // slot-layout start of this frame's content
+    bool complete;                      // read up to its EndMark (and content checksum); false: the container breaks off inside it
 };
 static constexpr uint64_t XXH_LONG_AVG = 32768;     // average stream length from which a whole warp per stream wins
 
@@ -41,6 +42,7 @@ struct FrameIndex {
     std::vector<FrameRec> frames;
     std::vector<BlockRec> blocks;
     uint64_t slot_bytes = 0;            // device bytes needed for the slot layout (upper bound of the decoded size)
+    int tail_err = 0;                   // the container's own error, behind everything indexed (reported after what precedes it)
     // device-side descriptor arrays, built once
     int device = -1;
     uint8_t* d_blob = nullptr; size_t blob_bytes = 0;
@@ -57,45 +59,52 @@ struct FrameIndex {
     std::vector<size_t> comp_ix, raw_ix, bsum_ix, fsum_ix;
 };
 
-// LZ4FrameInputStream.nextFrameInfo / readHeader / readBlock as a pure index pass
+// LZ4FrameInputStream.nextFrameInfo / readHeader / readBlock as a pure index pass.  The reader is a stream: it hands out the
+// bytes of every frame before a malformed spot and fails THERE, after any checksum or decode error that lies earlier.  So an
+// error behind at least one indexed frame is not returned here: it is kept in ix.tail_err, what precedes it is decoded and
+// verified like any other input (the blocks of a frame cut short included -- that frame has no content checks), and
+// decode_dev reports the first error in stream order.
 static int index_frames(const uint8_t* src, size_t n, FrameIndex& ix)
 {
     size_t ip = 0; bool seen = false;
-    while (ip < n) {
-        if (n - ip < 4) return -1;
+    int err = 0;
+    FrameRec f{};
+    auto stop = [&](int code) { err = code; };
+    while (ip < n && !err) {
+        if (n - ip < 4) { stop(-1); break; }
         const uint32_t magic = rd32(src + ip); ip += 4;
         if ((magic >> 4) == (0x184D2A50u >> 4)) {                               // skippable (:154,162-173)
-            if (n - ip < 4) return -1;
+            if (n - ip < 4) { stop(-1); break; }
             const uint32_t sz = rd32(src + ip); ip += 4;
-            if (n - ip < sz) return -1;
+            if (n - ip < sz) { stop(-1); break; }
             ip += sz; seen = true; continue;
         }
-        if (magic != 0x184D2204u) return -2;                                    // (:151)
-        FrameRec f{};
+        if (magic != 0x184D2204u) { stop(-2); break; }                          // (:151)
+        f = FrameRec{};
         f.desc_off = ip;
-        if (n - ip < 3) return -1;
+        if (n - ip < 3) { stop(-1); break; }
         f.flg = src[ip++]; const uint8_t bd = src[ip++];
-        if ((f.flg >> 6) != 1 || (f.flg & 2) || !(f.flg & 0x20) || (f.flg & 1)) return -10;   // version, reserved, B.Indep, dictID
-        if ((bd & 0x8F) || (bd >> 4) < 4) return -10;
+        if ((f.flg >> 6) != 1 || (f.flg & 2) || !(f.flg & 0x20) || (f.flg & 1)) { stop(-10); break; }   // version, reserved, B.Indep, dictID
+        if ((bd & 0x8F) || (bd >> 4) < 4) { stop(-10); break; }
         f.bs = 1u << (8 + 2 * (bd >> 4));
         f.has_size = f.flg & 8;
-        if (f.has_size) { if (n - ip < 9) return -1; f.content_size = (uint64_t)rd32(src + ip) | ((uint64_t)rd32(src + ip + 4) << 32); ip += 8; }
-        if (n - ip < 1) return -1;
+        if (f.has_size) { if (n - ip < 9) { stop(-1); break; } f.content_size = (uint64_t)rd32(src + ip) | ((uint64_t)rd32(src + ip + 4) << 32); ip += 8; }
+        if (n - ip < 1) { stop(-1); break; }
         f.desc_len = (int32_t)(ip - f.desc_off);
         f.hc_byte = src[ip++];
         f.first_block = ix.blocks.size();
         f.out_off = ix.slot_bytes;
         for (;;) {                                                              // readBlock (:258-321)
-            if (n - ip < 4) return -1;
+            if (n - ip < 4) { stop(-1); break; }
             const uint32_t word = rd32(src + ip); ip += 4;
             const uint32_t sz = word & 0x7FFFFFFFu;
             if (sz == 0) break;                                                 // EndMark
-            if (sz > f.bs) return -4;
+            if (sz > f.bs) { stop(-4); break; }
             BlockRec b{}; b.src_off = ip; b.size = sz; b.raw = word >> 31; b.frame = ix.frames.size();
-            if (n - ip < sz) return -1;
+            if (n - ip < sz) { stop(-1); break; }
             ip += sz;
             b.has_checksum = f.flg & 0x10;
-            if (b.has_checksum) { if (n - ip < 4) return -1; b.checksum = rd32(src + ip); ip += 4; }
+            if (b.has_checksum) { if (n - ip < 4) { stop(-1); break; } b.checksum = rd32(src + ip); ip += 4; }
             // the slot: a stored block needs its own size, a compressed one cannot decode to more than 255 bytes per byte
             // (one length byte adds at most 255) -- so a stream of tiny flushed blocks asks for what it can fill, not for
             // blockMaxSize each.  Full blocks keep exactly bs: a frame without short blocks in the middle stays contiguous.
@@ -105,9 +114,19 @@ static int index_frames(const uint8_t* src, size_t n, FrameIndex& ix)
             ix.blocks.push_back(b);
         }
         f.nblocks = ix.blocks.size() - f.first_block;
-        f.has_checksum = f.flg & 4;
-        if (f.has_checksum) { if (n - ip < 4) return -1; f.content_checksum = rd32(src + ip); ip += 4; }
+        f.complete = !err;
+        f.has_checksum = !err && (f.flg & 4);
+        if (f.has_checksum) {
+            if (n - ip < 4) { stop(-1); f.complete = false; f.has_checksum = false; }
+            else { f.content_checksum = rd32(src + ip); ip += 4; }
+        }
+        if (!f.complete) f.has_size = false;
         ix.frames.push_back(f); seen = true;
+    }
+    if (err) {
+        if (ix.frames.empty()) return err;                                      // nothing lies before the error
+        ix.tail_err = err;
+        return 0;
     }
     return seen ? 0 : -1;
 }
@@ -255,34 +274,36 @@ int64_t b200lz4f_decode_dev(void* index, const uint8_t* d_src, uint8_t* d_slots,
     if (ix.n_fsum && cudaMemcpyAsync(H + ix.o_f_out, D + ix.o_f_out, ix.n_fsum * 4, cudaMemcpyDeviceToHost, st) != cudaSuccess) return B200LZ4_E_CUDA;
     if (cudaStreamSynchronize(st) != cudaSuccess) return B200LZ4_E_CUDA;
 
-    for (size_t f = 0; f < nf; f++)
-        if ((( ((uint32_t*)(H + ix.o_h_out))[f] >> 8) & 0xFF) != ix.frames[f].hc_byte) return -3;      // (:208-216)
-    for (size_t k = 0; k < ix.n_bsum; k++)
-        if (((uint32_t*)(H + ix.o_b_out))[k] != ix.blocks[ix.bsum_ix[k]].checksum) return -5;          // (:298-303)
+    // the verdict, in the order the stream reader meets things: frame by frame -- descriptor hash (:208-216), then block by
+    // block its checksum (:298-303) and its decode (:307-311), then at the EndMark content checksum (:266-269) and size (:270-272)
+    std::vector<int32_t> bsum_of(ix.blocks.size(), -1), fsum_of(nf, -1);
+    for (size_t k = 0; k < ix.n_bsum; k++) bsum_of[ix.bsum_ix[k]] = (int32_t)k;
+    for (size_t k = 0; k < ix.n_fsum; k++) fsum_of[ix.fsum_ix[k]] = (int32_t)k;
+    const int32_t* blk_comp = (const int32_t*)(H + ix.o_k_comp);
     std::vector<int32_t> blen(ix.blocks.size());
-    for (size_t k = 0; k < ix.n_comp; k++) {
-        const int32_t r = ((int32_t*)(H + ix.o_c_res))[k];
-        if (r < 0) return -6;                                                                           // LZ4Exception -> IOException (:307-311)
-        blen[ix.comp_ix[k]] = r;
-    }
-    for (size_t k = 0; k < ix.n_raw; k++) blen[ix.raw_ix[k]] = (int32_t)ix.blocks[ix.raw_ix[k]].size;
-    if (block_len_out) memcpy(block_len_out, blen.data(), blen.size() * sizeof(int32_t));
     int64_t total = 0; bool gaps = false;
     for (size_t f = 0; f < nf; f++) {
         const FrameRec& fr = ix.frames[f];
+        if (((((uint32_t*)(H + ix.o_h_out))[f] >> 8) & 0xFF) != fr.hc_byte) return -3;
         uint64_t len = 0;
         for (size_t k = 0; k < fr.nblocks; k++) {
-            const int32_t l = blen[fr.first_block + k];
-            if (k + 1 < fr.nblocks && (uint32_t)l != fr.bs) gaps = true;      // a short block in the middle of a frame
+            const size_t b = fr.first_block + k;
+            const BlockRec& br = ix.blocks[b];
+            if (bsum_of[b] >= 0 && ((uint32_t*)(H + ix.o_b_out))[bsum_of[b]] != br.checksum) return -5;
+            int32_t l = (int32_t)br.size;
+            if (!br.raw) { l = ((int32_t*)(H + ix.o_c_res))[blk_comp[b]]; if (l < 0) return -6; }   // LZ4Exception -> IOException
+            blen[b] = l;
+            if (k + 1 < fr.nblocks && (uint32_t)l != fr.bs) gaps = true;          // a short block in the middle of a frame
             len += (uint64_t)l;
         }
-        if (fr.has_size && fr.content_size != len) return -8;                                           // (:270-272)
+        if (fsum_of[f] >= 0 && ((uint32_t*)(H + ix.o_f_out))[fsum_of[f]] != fr.content_checksum) return -7;
+        if (fr.has_size && fr.content_size != len) return -8;
         if (frame_off) frame_off[f] = fr.out_off;
         if (frame_len) frame_len[f] = len;
         total += (int64_t)len;
     }
-    for (size_t k = 0; k < ix.n_fsum; k++)
-        if (((uint32_t*)(H + ix.o_f_out))[k] != ix.frames[ix.fsum_ix[k]].content_checksum) return -7;   // (:266-269)
+    if (ix.tail_err) return ix.tail_err;                    // the container breaks off / is malformed behind all that
+    if (block_len_out) memcpy(block_len_out, blen.data(), blen.size() * sizeof(int32_t));
     return gaps ? -11 : total;                              // -11: everything verified, but read the blocks one by one
 }
 

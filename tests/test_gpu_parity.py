@@ -696,6 +696,74 @@ def test_frames_written_with_flush(b200, port):
     N.lib().b200lz4f_index_free(ix); N.lib().b200lz4f_index_free(ix2)
 
 
+def test_frame_errors_come_in_stream_order(b200, port):
+    """LZ4FrameInputStream is a stream: of several things wrong with a container it reports the FIRST one it meets
+    (descriptor hash, then block by block checksum and decode, then at the EndMark content checksum before content size,
+    LZ4FrameInputStream.java:208-216, 264-273, 298-311), and a container cut short or malformed further on still fails
+    on an earlier checksum first.  One to three random faults per container, against the restated sequential reader."""
+    rng = random.Random(2024)
+    base = port.datagen(1 << 18, 0.5, 0.0, 21).tobytes()
+    sim = "sim" in os.environ.get("B200LZ4_TEST_SO", "")
+    seen = {}
+    for trial in range(int(os.environ.get("B200_TRIALS", 60 if sim else 400))):
+        frames = []
+        for _ in range(rng.randrange(1, 4)):
+            pieces = [base[o:o + n] for o, n in ((rng.randrange(0, 100000), rng.choice((1, 40, 700, 5000, 65536))) for _ in range(rng.randrange(0, 5)))]
+            if rng.random() < 0.5:
+                body = b"".join(pieces)
+                frames.append(port.frame_compress(body, rng.choice((4, 5)), rng.randrange(8)))   # flags: content checksum, block checksums, content size
+            else:
+                frames.append(_frame_of_pieces(port, pieces, rng.choice((4, 5)), content_checksum=rng.random() < 0.7, block_checksum=rng.random() < 0.5,
+                                               stored={i for i in range(len(pieces)) if rng.random() < 0.2}))
+        blob = bytearray(b"".join(frames))
+        total = 1 << 20
+        for _ in range(rng.randrange(1, 4)):
+            kind = rng.randrange(4)
+            if kind == 0 and len(blob) > 8:
+                del blob[rng.randrange(len(blob) - 8, len(blob)):]                   # cut short near the end
+            elif kind == 1 and len(blob) > 1:
+                del blob[rng.randrange(1, len(blob)):]                               # cut short anywhere
+            elif blob:
+                i = rng.randrange(len(blob)); blob[i] ^= 1 << rng.randrange(8)       # one flipped bit
+        want, out = port.frame_decompress(bytes(blob), total)
+        if want >= 0:
+            assert b200.decompress_frames(bytes(blob), total) == out, trial
+            seen["ok"] = seen.get("ok", 0) + 1
+            continue
+        with pytest.raises(b200.LZ4FrameError) as e:
+            b200.decompress_frames(bytes(blob), total)
+        assert e.value.code == want, (trial, e.value.code, want, bytes(blob).hex() if len(blob) < 400 else len(blob))
+        seen[want] = seen.get(want, 0) + 1
+    assert len([k for k in seen if k != "ok"]) >= (4 if sim else 6), seen              # the sweep met most of the codes
+    # the same for lz4-java's own container (LZ4BlockInputStream.java:191-264): premature end vs "Stream is corrupted" vs our -9
+    seen = {}
+    for trial in range(int(os.environ.get("B200_TRIALS", 60 if sim else 400))):
+        body = b"".join(base[o:o + n] for o, n in ((rng.randrange(0, 100000), rng.choice((1, 40, 700, 5000, 70000))) for _ in range(rng.randrange(0, 4))))
+        if rng.random() < 0.2:
+            body += rng.randbytes(3000)                                              # a stored block
+        blob = bytearray(port.lz4block_compress(body, rng.choice((64, 4096, 65536))))
+        for _ in range(rng.randrange(1, 4)):
+            kind = rng.randrange(3)
+            if kind == 0 and len(blob) > 1:
+                del blob[rng.randrange(1, len(blob)):]
+            elif blob:
+                i = rng.randrange(len(blob)); blob[i] ^= 1 << rng.randrange(8)
+        stop = rng.random() < 0.7
+        cap = len(body) + rng.choice((0, 0, 8, -1000))
+        cap = max(cap, 0)
+        want, out = port.lz4block_decompress(bytes(blob), cap, stop)
+        if want >= 0:
+            assert b200.decompress_lz4block(bytes(blob), cap, stop_on_empty_block=stop) == out, trial
+            seen["ok"] = seen.get("ok", 0) + 1
+            continue
+        with pytest.raises((EOFError, IOError)) as e:
+            b200.decompress_lz4block(bytes(blob), cap, stop_on_empty_block=stop)
+        got = -1 if isinstance(e.value, EOFError) else (-2 if "corrupted" in str(e.value) else -9)
+        assert got == want, (trial, got, want, str(e.value))
+        seen[want] = seen.get(want, 0) + 1
+    assert len(seen) >= 3, seen
+
+
 def test_frame_writer_and_lz4java_containers(b200, port):
     """(f)-2..4: frames / LZ4Block streams / length-prefixed blocks WRITTEN on the GPU path are read by the CPU
     restatements (and by the reference's LZ4F_decompress when available), and vice versa"""

@@ -351,6 +351,6 @@ def test_host_layer_on_the_emulator_library():
     # 1 MiB pipeline chunks: the 40-block batches of these tests then cross chunk boundaries (all three stream slots in use)
     env = dict(os.environ, B200LZ4_TEST_SO=os.path.join(HERE, "simt", "_build", "libb200lz4_sim.so"), B200LZ4_CHUNK_MB="1", SIMT_DEVICES="3")
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(HERE, "test_gpu_parity.py"), "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider",
-                        "-W", "ignore::DeprecationWarning", "-k", "factory_api or compact_host or xxhash_streaming or self_roundtrip or failed_pipeline or contexts_are_reused or jni_shim or multi_gpu_range or written_with_flush or device_side_compaction"],
+                        "-W", "ignore::DeprecationWarning", "-k", "factory_api or compact_host or xxhash_streaming or self_roundtrip or failed_pipeline or contexts_are_reused or jni_shim or multi_gpu_range or written_with_flush or device_side_compaction or stream_order"],
                        env=env, cwd=ROOT, capture_output=True, text=True)
-    assert r.returncode == 0 and "10 passed" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.returncode == 0 and "11 passed" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
