@@ -213,6 +213,14 @@ int b200xxh64_batch_host_multi(const uint8_t* base, const uint64_t* off, const i
  * blockMaxSize for a stream of tiny blocks. */
 int64_t b200lz4f_decompress_host(const uint8_t* src, size_t srcSize, uint8_t* dst, size_t dstCapacity);
 void*   b200lz4f_index_create(const uint8_t* src_host, size_t srcSize, uint64_t* slot_bytes, int* err);
+/* readSingleFrame = true (LZ4FrameInputStream.java:83-91,118-123): reading stops behind the first non-skippable frame, the
+ * rest of src is not looked at; *src_consumed (may be NULL) = how far the reader got. */
+int64_t b200lz4f_decompress_host_single(const uint8_t* src, size_t srcSize, uint8_t* dst, size_t dstCapacity, size_t* src_consumed);
+void*   b200lz4f_index_create_single(const uint8_t* src_host, size_t srcSize, uint64_t* slot_bytes, size_t* src_consumed, int* err);
+/* getExpectedContentSize / isExpectedContentSizeDefined (:416-445): *content_size = what the first non-skippable frame's
+ * descriptor declares, -1 if it declares none (or there are only skippable frames).  Returns 0 or a code from the list above
+ * (the descriptor hash is checked, on the device like every hash here). */
+int     b200lz4f_expected_content_size(const uint8_t* src, size_t srcSize, int64_t* content_size);
 size_t  b200lz4f_index_frames(void* index);
 size_t  b200lz4f_index_blocks(void* index);
 void    b200lz4f_index_block_offsets(void* index, uint64_t* block_off);   /* b200lz4f_index_blocks() entries, bytes into d_slots */

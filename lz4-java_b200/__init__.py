@@ -10,10 +10,10 @@ from .lz4 import (LZ4Factory, LZ4Compressor, LZ4FastDecompressor, LZ4SafeDecompr
 from .xxhash import XXHashFactory, XXHash32, XXHash64, StreamingXXHash32, StreamingXXHash64
 from . import batch
 from . import frame
-from .frame import (decompress_frames, compress_frame, compress_lz4block, decompress_lz4block,
+from .frame import (decompress_frames, expected_content_size, compress_frame, compress_lz4block, decompress_lz4block,
                     compress_with_length, decompress_with_length, LZ4FrameError)
 
 __all__ = ["LZ4Factory", "LZ4Compressor", "LZ4FastDecompressor", "LZ4SafeDecompressor", "LZ4Exception",
            "XXHashFactory", "XXHash32", "XXHash64", "StreamingXXHash32", "StreamingXXHash64",
            "max_compressed_length", "batch", "B200Error", "frame", "decompress_frames", "compress_frame", "compress_lz4block",
-           "decompress_lz4block", "compress_with_length", "decompress_with_length", "LZ4FrameError"]
+           "decompress_lz4block", "expected_content_size", "compress_with_length", "decompress_with_length", "LZ4FrameError"]

@@ -65,6 +65,9 @@ SYMBOLS = [
     ("b200lz4_compress_fast_compact_host", _i, [_vp, _vp, _vp, _vp, _sz, _vp, _vp, _sz, _i, _vp]),
     ("b200lz4f_decompress_host", C.c_int64, [_vp, _sz, _vp, _sz]),
     ("b200lz4f_index_create", _vp, [_vp, _sz, _vp, _vp]),
+    ("b200lz4f_index_create_single", _vp, [_vp, _sz, _vp, _vp, _vp]),
+    ("b200lz4f_decompress_host_single", C.c_int64, [_vp, _sz, _vp, _sz, _vp]),
+    ("b200lz4f_expected_content_size", _i, [_vp, _sz, _vp]),
     ("b200lz4f_index_frames", _sz, [_vp]),
     ("b200lz4f_index_blocks", _sz, [_vp]),
     ("b200lz4f_index_block_offsets", None, [_vp, _vp]),

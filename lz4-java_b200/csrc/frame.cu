@@ -64,7 +64,7 @@ struct FrameIndex {
 // error behind at least one indexed frame is not returned here: it is kept in ix.tail_err, what precedes it is decoded and
 // verified like any other input (the blocks of a frame cut short included -- that frame has no content checks), and
 // decode_dev reports the first error in stream order.
-static int index_frames(const uint8_t* src, size_t n, FrameIndex& ix)
+static int index_frames(const uint8_t* src, size_t n, FrameIndex& ix, bool single = false, size_t* consumed = nullptr)
 {
     size_t ip = 0; bool seen = false;
     int err = 0;
@@ -122,7 +122,9 @@ static int index_frames(const uint8_t* src, size_t n, FrameIndex& ix)
         }
         if (!f.complete) f.has_size = false;
         ix.frames.push_back(f); seen = true;
+        if (single) break;                                                      // readSingleFrame (:83-91, 327, 346): the rest is not read
     }
+    if (consumed) *consumed = ip;
     if (err) {
         if (ix.frames.empty()) return err;                                      // nothing lies before the error
         ix.tail_err = err;
@@ -189,16 +191,55 @@ using namespace b200;
 
 extern "C" {
 
-void* b200lz4f_index_create(const uint8_t* src_host, size_t n, uint64_t* slot_bytes, int* err)
+static void* index_create(const uint8_t* src_host, size_t n, bool single, uint64_t* slot_bytes, size_t* consumed, int* err)
 {
     FrameIndex* ix = new (std::nothrow) FrameIndex();
     if (!ix) { if (err) *err = B200LZ4_E_ARG; return nullptr; }
-    int rc = src_host ? index_frames(src_host, n, *ix) : -1;
+    int rc = src_host ? index_frames(src_host, n, *ix, single, consumed) : -1;
     if (rc == 0) rc = build_descriptors(*ix);
     if (rc) { delete ix; if (err) *err = rc; return nullptr; }
     if (slot_bytes) *slot_bytes = ix->slot_bytes;
     if (err) *err = 0;
     return ix;
+}
+
+void* b200lz4f_index_create(const uint8_t* src_host, size_t n, uint64_t* slot_bytes, int* err)
+{ return index_create(src_host, n, false, slot_bytes, nullptr, err); }
+void* b200lz4f_index_create_single(const uint8_t* src_host, size_t n, uint64_t* slot_bytes, size_t* src_consumed, int* err)
+{ return index_create(src_host, n, true, slot_bytes, src_consumed, err); }
+
+// getExpectedContentSize / isExpectedContentSizeDefined (:416-445): the content size the first non-skippable frame declares,
+// -1 when it declares none or when there is no frame at all; the descriptor hash is verified like nextFrameInfo does.
+int b200lz4f_expected_content_size(const uint8_t* src, size_t n, int64_t* content_size)
+{
+    if (!src || !content_size) return B200LZ4_E_ARG;
+    *content_size = -1;
+    size_t ip = 0; bool seen = false;
+    for (;;) {
+        if (n - ip < 4) return (seen && n == ip) ? 0 : -1;                      // clean end behind skippable frames: "no frame" (:141-147)
+        const uint32_t magic = rd32(src + ip); ip += 4;
+        if ((magic >> 4) == (0x184D2A50u >> 4)) {
+            if (n - ip < 4) return -1;
+            const uint32_t sz = rd32(src + ip); ip += 4;
+            if (n - ip < sz) return -1;
+            ip += sz; seen = true; continue;
+        }
+        if (magic != 0x184D2204u) return -2;
+        const size_t desc = ip;
+        if (n - ip < 2) return -1;
+        const uint8_t flg = src[ip++], bd = src[ip++];
+        if ((flg >> 6) != 1 || (flg & 2) || !(flg & 0x20) || (flg & 1)) return -10;
+        if ((bd & 0x8F) || (bd >> 4) < 4) return -10;
+        uint64_t size = 0;
+        if (flg & 8) { if (n - ip < 8) return -1; size = (uint64_t)rd32(src + ip) | ((uint64_t)rd32(src + ip + 4) << 32); ip += 8; }
+        if (n - ip < 1) return -1;
+        const uint32_t h = b200xxh32(src + desc, ip - desc, 0);
+        const int st = b200lz4_last_status();
+        if (st) return st;
+        if (((h >> 8) & 0xFF) != src[ip]) return -3;
+        if (flg & 8) *content_size = (int64_t)size;
+        return 0;
+    }
 }
 
 void b200lz4f_index_free(void* index)
@@ -316,10 +357,10 @@ void b200lz4f_index_block_offsets(void* index, uint64_t* block_off)
 }
 
 // Whole thing with HOST buffers: index, upload, decode, download frame by frame into one contiguous stream.
-int64_t b200lz4f_decompress_host(const uint8_t* src, size_t n, uint8_t* dst, size_t dst_capacity)
+static int64_t decompress_host(const uint8_t* src, size_t n, uint8_t* dst, size_t dst_capacity, bool single, size_t* consumed)
 {
     int err = 0; uint64_t slot_bytes = 0;
-    void* index = b200lz4f_index_create(src, n, &slot_bytes, &err);
+    void* index = index_create(src, n, single, &slot_bytes, consumed, &err);
     if (!index) return err;
     FrameIndex& ix = *(FrameIndex*)index;
     int64_t rc = 0;
@@ -373,5 +414,11 @@ int64_t b200lz4f_decompress_host(const uint8_t* src, size_t n, uint8_t* dst, siz
     b200lz4f_index_free(index);
     return rc;
 }
+
+int64_t b200lz4f_decompress_host(const uint8_t* src, size_t n, uint8_t* dst, size_t dst_capacity)
+{ return decompress_host(src, n, dst, dst_capacity, false, nullptr); }
+// LZ4FrameInputStream(in, readSingleFrame = true): the first non-skippable frame only; *src_consumed = where it ended
+int64_t b200lz4f_decompress_host_single(const uint8_t* src, size_t n, uint8_t* dst, size_t dst_capacity, size_t* src_consumed)
+{ return decompress_host(src, n, dst, dst_capacity, true, src_consumed); }
 
 } // extern "C"

@@ -33,15 +33,31 @@ class LZ4FrameError(IOError):
         self.code = code
 
 
-def decompress_frames(src, max_decoded: int) -> bytes:
-    """decode every frame in `src` (concatenated / skippable frames allowed) -> the decoded stream"""
+def decompress_frames(src, max_decoded: int, read_single_frame: bool = False) -> bytes:
+    """decode every frame in `src` (concatenated / skippable frames allowed) -> the decoded stream;
+    read_single_frame: stop behind the first non-skippable frame like LZ4FrameInputStream(in, true) (:83-91)"""
     s = _view(src)
     out = np.empty(max(max_decoded, 1), dtype=np.uint8)
-    r = N.lib().b200lz4f_decompress_host(s.ctypes.data, len(s), out.ctypes.data, max_decoded)
+    if read_single_frame:
+        r = N.lib().b200lz4f_decompress_host_single(s.ctypes.data, len(s), out.ctypes.data, max_decoded, None)
+    else:
+        r = N.lib().b200lz4f_decompress_host(s.ctypes.data, len(s), out.ctypes.data, max_decoded)
     N.check(r)
     if r < 0:
         raise LZ4FrameError(int(r))
     return out[:r].tobytes()
+
+
+def expected_content_size(src) -> int:
+    """LZ4FrameInputStream.getExpectedContentSize (:416-428): the content size the first non-skippable frame declares, -1 if none"""
+    import ctypes
+    s = _view(src)
+    size = ctypes.c_int64(-1)
+    r = N.lib().b200lz4f_expected_content_size(s.ctypes.data, len(s), ctypes.byref(size))
+    N.check(r)
+    if r < 0:
+        raise LZ4FrameError(int(r))
+    return int(size.value)
 
 
 def compress_frame(src, block_size_code: int = 4, content_checksum=True, block_checksum=False, content_size=False) -> bytes:

@@ -696,6 +696,43 @@ def test_frames_written_with_flush(b200, port):
     N.lib().b200lz4f_index_free(ix); N.lib().b200lz4f_index_free(ix2)
 
 
+def test_read_single_frame_and_expected_content_size(b200, port):
+    """LZ4FrameIOStreamTest.java:310-426: a frame written with its content size reports it (getExpectedContentSize), one
+    written without reports -1; with readSingleFrame the reader stops behind the first non-skippable frame -- four
+    concatenated copies yield one -- and says how far it read; what follows that frame is not even looked at."""
+    import ctypes
+    data = port.datagen(300000, 0.5, 0.0, 77).tobytes()
+    with_size = b200.compress_frame(data, 7, True, False, True)
+    without = b200.compress_frame(data, 7, True, False, False)
+    assert b200.expected_content_size(with_size) == len(data)                      # :326-329
+    assert b200.expected_content_size(port.frame_compress(data, 4, 5)) == len(data)
+    assert b200.expected_content_size(without) == -1                               # :348-351
+    assert b200.decompress_frames(with_size, len(data), read_single_frame=True) == data
+    four = without * 4                                                              # :379-420
+    assert b200.decompress_frames(four, 4 * len(data)) == data * 4
+    assert b200.decompress_frames(four, 4 * len(data), read_single_frame=True) == data
+    assert b200.expected_content_size(four) == -1
+    skip = bytes([0x5A, 0x2A, 0x4D, 0x18, 3, 0, 0, 0, 9, 9, 9])
+    lead = skip + skip + with_size + b"\x00garbage that is not a frame"
+    assert b200.decompress_frames(lead, len(data), read_single_frame=True) == data  # skippable frames do not count as "the" frame
+    assert b200.expected_content_size(lead) == len(data)
+    with pytest.raises(b200.LZ4FrameError) as e:
+        b200.decompress_frames(lead, len(data))                                     # ... the multi-frame reader trips over the rest
+    assert e.value.code == -2
+    L = b200._native.lib()
+    buf = np.frombuffer(lead, dtype=np.uint8); out = np.zeros(len(data), dtype=np.uint8); used = ctypes.c_size_t(0)
+    assert L.b200lz4f_decompress_host_single(buf.ctypes.data, len(buf), out.ctypes.data, len(out), ctypes.byref(used)) == len(data)
+    assert used.value == 2 * len(skip) + len(with_size) and out.tobytes() == data
+    assert b200.expected_content_size(skip) == -1                                   # only skippable frames: no frame, no error (:141-147)
+    assert b200.decompress_frames(skip, 10, read_single_frame=True) == b""
+    for bad, code in ((b"", -1), (skip + b"\x04\x22", -1), (b"\x04\x22\x4d\x18\x60", -1), (b"\x01\x02\x03\x04rest", -2),
+                      (with_size[:4] + bytes([with_size[4] ^ 0x80]) + with_size[5:], -10),
+                      (with_size[:7] + bytes([with_size[7] ^ 1]) + with_size[8:], -3)):      # a bit of the content size: descriptor hash
+        with pytest.raises(b200.LZ4FrameError) as e:
+            b200.expected_content_size(bad)
+        assert e.value.code == code, (bad[:12], e.value.code, code)
+
+
 def test_frame_errors_come_in_stream_order(b200, port):
     """LZ4FrameInputStream is a stream: of several things wrong with a container it reports the FIRST one it meets
     (descriptor hash, then block by block checksum and decode, then at the EndMark content checksum before content size,
