@@ -237,8 +237,12 @@ void    b200lz4f_index_free(void* index);
  * Return: bytes written / decoded, or negative: -1 premature end, -2 corrupted, -9 dst too small, B200LZ4_E_*. */
 size_t  b200lz4f_compress_bound(size_t srcSize, int bsCode);
 int64_t b200lz4f_compress_host(const uint8_t* src, size_t srcSize, uint8_t* dst, size_t dstCapacity, int bsCode, int flags);
+/* the writers' LZ4Compressor argument (LZ4FrameOutputStream.java:132-133, LZ4BlockOutputStream.java:96,124): hc_level 0 = the
+ * fast compressor (what the calls without _hc use), 1..17 = LZ4_compress_HC at that level */
+int64_t b200lz4f_compress_host_hc(const uint8_t* src, size_t srcSize, uint8_t* dst, size_t dstCapacity, int bsCode, int flags, int hc_level);
 size_t  b200lz4block_compress_bound(size_t srcSize, int blockSize);
 int64_t b200lz4block_compress_host(const uint8_t* src, size_t srcSize, uint8_t* dst, size_t dstCapacity, int blockSize);
+int64_t b200lz4block_compress_host_hc(const uint8_t* src, size_t srcSize, uint8_t* dst, size_t dstCapacity, int blockSize, int hc_level);
 /* stopOnEmptyBlock: LZ4BlockInputStream's constructor flag (LZ4BlockInputStream.java:60-72; its default is true): non-zero
  * ends at the first empty block and reports in *srcConsumed (may be NULL) how far it read; zero steps over empty blocks and
  * reads concatenated streams to the end of src. */

@@ -75,8 +75,10 @@ SYMBOLS = [
     ("b200lz4f_index_free", None, [_vp]),
     ("b200lz4f_compress_bound", _sz, [_sz, _i]),
     ("b200lz4f_compress_host", C.c_int64, [_vp, _sz, _vp, _sz, _i, _i]),
+    ("b200lz4f_compress_host_hc", C.c_int64, [_vp, _sz, _vp, _sz, _i, _i, _i]),
     ("b200lz4block_compress_bound", _sz, [_sz, _i]),
     ("b200lz4block_compress_host", C.c_int64, [_vp, _sz, _vp, _sz, _i]),
+    ("b200lz4block_compress_host_hc", C.c_int64, [_vp, _sz, _vp, _sz, _i, _i]),
     ("b200lz4block_decompress_host", C.c_int64, [_vp, _sz, _vp, _sz, C.c_int, _vp]),
     ("b200lz4_compress_with_length", _i, [_vp, _vp, _i, _i]),
     ("b200lz4_decompressed_length", _i, [_vp]),

@@ -15,6 +15,22 @@
 static inline void put32(uint8_t* p, uint32_t v) { p[0] = (uint8_t)v; p[1] = (uint8_t)(v >> 8); p[2] = (uint8_t)(v >> 16); p[3] = (uint8_t)(v >> 24); }
 static inline uint32_t get32(const uint8_t* p) { return p[0] | (p[1] << 8) | (p[2] << 16) | ((uint32_t)p[3] << 24); }
 
+// The writers' compressor argument (LZ4FrameOutputStream / LZ4BlockOutputStream take any LZ4Compressor): hc_level 0 = the fast
+// compressor, packed output; 1..17 = LZ4_compress_HC at that level into bound-sized slots.  coff/clen as *_compact_host.
+static int compress_blocks(const uint8_t* src, const uint64_t* soff, const int32_t* slen, uint8_t* tmp, size_t tmp_cap,
+                           uint64_t* coff, int32_t* clen, size_t nb, int max_src_len, int hc_level)
+{
+    if (hc_level <= 0) {
+        uint64_t total = 0;
+        return b200lz4_compress_fast_compact_host(src, soff, slen, tmp, tmp_cap, coff, clen, nb, max_src_len, &total);
+    }
+    std::vector<int32_t> ccap(nb);
+    uint64_t acc = 0;
+    for (size_t i = 0; i < nb; i++) { coff[i] = acc; ccap[i] = slen[i] + slen[i] / 255 + 16; acc += ((uint64_t)ccap[i] + 15) & ~uint64_t(15); }
+    if (acc > tmp_cap) return B200LZ4_E_ARG;
+    return b200lz4_compress_hc_batch_host(src, soff, slen, tmp, coff, ccap.data(), clen, nb, hc_level);
+}
+
 extern "C" {
 
 size_t b200lz4f_compress_bound(size_t n, int bsCode)
@@ -25,7 +41,7 @@ size_t b200lz4f_compress_bound(size_t n, int bsCode)
 }
 
 // flags: bit0 content checksum, bit1 block checksums, bit2 content size.  Returns bytes written or a negative code.
-int64_t b200lz4f_compress_host(const uint8_t* src, size_t n, uint8_t* dst, size_t cap, int bsCode, int flags)
+int64_t b200lz4f_compress_host_hc(const uint8_t* src, size_t n, uint8_t* dst, size_t cap, int bsCode, int flags, int hc_level)
 {
     if (bsCode < 4 || bsCode > 7) return B200LZ4_E_ARG;
     if (cap < b200lz4f_compress_bound(n, bsCode)) return -9;
@@ -43,12 +59,10 @@ int64_t b200lz4f_compress_host(const uint8_t* src, size_t n, uint8_t* dst, size_
         std::vector<uint64_t> soff(nb), coff(nb), poff(nb);
         std::vector<int32_t> slen(nb), clen(nb), plen(nb);
         for (size_t i = 0; i < nb; i++) { soff[i] = i * bs; slen[i] = (int32_t)((n - i * bs) < bs ? (n - i * bs) : bs); }
-        size_t tmp_cap = 0; for (size_t i = 0; i < nb; i++) tmp_cap += (size_t)slen[i] + slen[i] / 255 + 16;
+        size_t tmp_cap = 0; for (size_t i = 0; i < nb; i++) tmp_cap += (size_t)slen[i] + slen[i] / 255 + 32;
         uint8_t* tmp = (uint8_t*)malloc(tmp_cap ? tmp_cap : 1);
         if (!tmp) return B200LZ4_E_ARG;
-        uint64_t total = 0;
-        int rc = b200lz4_compress_fast_compact_host(src, soff.data(), slen.data(), tmp, tmp_cap, coff.data(), clen.data(), nb,
-                                                    bs <= 65536 ? 65536 : 0, &total);
+        int rc = compress_blocks(src, soff.data(), slen.data(), tmp, tmp_cap, coff.data(), clen.data(), nb, bs <= 65536 ? 65536 : 0, hc_level);
         if (rc) { free(tmp); return rc; }
         for (size_t i = 0; i < nb; i++) {                                        // writeBlock (:199-235)
             const bool raw = clen[i] <= 0 || clen[i] >= slen[i];                 // stored uncompressed when it does not shrink (:215-222)
@@ -73,6 +87,8 @@ int64_t b200lz4f_compress_host(const uint8_t* src, size_t n, uint8_t* dst, size_
     }
     return (int64_t)o;
 }
+int64_t b200lz4f_compress_host(const uint8_t* src, size_t n, uint8_t* dst, size_t cap, int bsCode, int flags)
+{ return b200lz4f_compress_host_hc(src, n, dst, cap, bsCode, flags, 0); }
 
 // ---------------------------------------------------------------- "LZ4Block" container
 static const uint8_t LZ4BLOCK_MAGIC[8] = { 'L', 'Z', '4', 'B', 'l', 'o', 'c', 'k' };
@@ -92,7 +108,7 @@ size_t b200lz4block_compress_bound(size_t n, int blockSize)
     return (nb + 1) * LZ4BLOCK_HEADER + n + nb * 16 + n / 255;
 }
 
-int64_t b200lz4block_compress_host(const uint8_t* src, size_t n, uint8_t* dst, size_t cap, int blockSize)
+int64_t b200lz4block_compress_host_hc(const uint8_t* src, size_t n, uint8_t* dst, size_t cap, int blockSize, int hc_level)
 {
     if (blockSize < 64 || blockSize > (1 << 25)) return B200LZ4_E_ARG;
     if (cap < b200lz4block_compress_bound(n, blockSize)) return -9;
@@ -104,12 +120,10 @@ int64_t b200lz4block_compress_host(const uint8_t* src, size_t n, uint8_t* dst, s
         std::vector<int32_t> slen(nb), clen(nb);
         std::vector<uint32_t> sums(nb);
         for (size_t i = 0; i < nb; i++) { soff[i] = i * bs; slen[i] = (int32_t)((n - i * bs) < bs ? (n - i * bs) : bs); }
-        size_t tmp_cap = 0; for (size_t i = 0; i < nb; i++) tmp_cap += (size_t)slen[i] + slen[i] / 255 + 16;
+        size_t tmp_cap = 0; for (size_t i = 0; i < nb; i++) tmp_cap += (size_t)slen[i] + slen[i] / 255 + 32;
         uint8_t* tmp = (uint8_t*)malloc(tmp_cap ? tmp_cap : 1);
         if (!tmp) return B200LZ4_E_ARG;
-        uint64_t total = 0;
-        int rc = b200lz4_compress_fast_compact_host(src, soff.data(), slen.data(), tmp, tmp_cap, coff.data(), clen.data(), nb,
-                                                    bs <= 65536 ? 65536 : 0, &total);
+        int rc = compress_blocks(src, soff.data(), slen.data(), tmp, tmp_cap, coff.data(), clen.data(), nb, bs <= 65536 ? 65536 : 0, hc_level);
         if (!rc) rc = b200xxh32_batch_host(src, soff.data(), slen.data(), LZ4BLOCK_SEED, sums.data(), nb);   // checksum of the ORIGINAL bytes
         if (rc) { free(tmp); return rc; }
         for (size_t i = 0; i < nb; i++) {                                        // flushBufferedData (:203-227)
@@ -130,6 +144,8 @@ int64_t b200lz4block_compress_host(const uint8_t* src, size_t n, uint8_t* dst, s
     o += LZ4BLOCK_HEADER;
     return (int64_t)o;
 }
+int64_t b200lz4block_compress_host(const uint8_t* src, size_t n, uint8_t* dst, size_t cap, int blockSize)
+{ return b200lz4block_compress_host_hc(src, n, dst, cap, blockSize, 0); }
 
 // Decodes an LZ4Block stream the way LZ4BlockInputStream reads it.  stopOnEmptyBlock != 0 (the reference's default, :100-104):
 // reading ends at the first empty block, whatever follows is left alone (*srcConsumed says where), and a stream that ends

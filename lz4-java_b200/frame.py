@@ -60,8 +60,9 @@ def expected_content_size(src) -> int:
     return int(size.value)
 
 
-def compress_frame(src, block_size_code: int = 4, content_checksum=True, block_checksum=False, content_size=False) -> bytes:
-    """one LZ4 frame as LZ4FrameOutputStream writes it (LZ4FrameOutputStream.java:178-251), whole buffer at once"""
+def compress_frame(src, block_size_code: int = 4, content_checksum=True, block_checksum=False, content_size=False, hc_level: int = 0) -> bytes:
+    """one LZ4 frame as LZ4FrameOutputStream writes it (LZ4FrameOutputStream.java:178-251), whole buffer at once;
+    hc_level: the stream's compressor argument (:132-133) -- 0 = fastCompressor(), 1..17 = highCompressor(level)"""
     s = _view(src)
     flags = (1 if content_checksum else 0) | (2 if block_checksum else 0) | (4 if content_size else 0)
     L = N.lib()
@@ -69,7 +70,7 @@ def compress_frame(src, block_size_code: int = 4, content_checksum=True, block_c
     if cap == 0:
         raise ValueError("block_size_code must be 4..7 (64 KiB .. 4 MiB)")
     out = np.empty(cap, dtype=np.uint8)
-    r = L.b200lz4f_compress_host(s.ctypes.data, len(s), out.ctypes.data, cap, block_size_code, flags)
+    r = L.b200lz4f_compress_host_hc(s.ctypes.data, len(s), out.ctypes.data, cap, block_size_code, flags, hc_level)
     N.check(r)
     if r < 0:
         raise LZ4FrameError(int(r))
@@ -77,14 +78,14 @@ def compress_frame(src, block_size_code: int = 4, content_checksum=True, block_c
 
 
 # ---- lz4-java's private "LZ4Block" container (LZ4BlockOutputStream / LZ4BlockInputStream)
-def compress_lz4block(src, block_size: int = 1 << 16) -> bytes:
+def compress_lz4block(src, block_size: int = 1 << 16, hc_level: int = 0) -> bytes:
     s = _view(src)
     L = N.lib()
     cap = L.b200lz4block_compress_bound(len(s), block_size)
     if cap == 0:
         raise ValueError("blockSize must be >= 64 and <= 32 MiB")            # LZ4BlockOutputStream.java:58-66
     out = np.empty(cap, dtype=np.uint8)
-    r = L.b200lz4block_compress_host(s.ctypes.data, len(s), out.ctypes.data, cap, block_size)
+    r = L.b200lz4block_compress_host_hc(s.ctypes.data, len(s), out.ctypes.data, cap, block_size, hc_level)
     N.check(r)
     if r < 0:
         raise LZ4FrameError(int(r))

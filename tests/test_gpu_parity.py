@@ -696,6 +696,34 @@ def test_frames_written_with_flush(b200, port):
     N.lib().b200lz4f_index_free(ix); N.lib().b200lz4f_index_free(ix2)
 
 
+def test_container_writers_with_the_high_compressor(b200, port):
+    """LZ4FrameOutputStream / LZ4BlockOutputStream take the compressor as an argument (LZ4FrameOutputStream.java:132-133,
+    LZ4BlockOutputStream.java:96,124); with highCompressor(level) the containers must still be read by the sequential readers
+    (restated, and the reference's LZ4F_decompress when it is there), and must not come out larger than with the fast one."""
+    from oracle import oracle as O
+    try:
+        ref = O.Ref()
+    except (FileNotFoundError, OSError):
+        ref = None
+    sim = "sim" in os.environ.get("B200LZ4_TEST_SO", "")
+    for n in ((1, 70000) if sim else (0, 1, 65536, 200000, 1500000)):
+        data = port.datagen(n, 0.5, 0.0, 5).tobytes()
+        for level in ((9,) if sim else (1, 9, 17)):
+            f_fast, f_hc = b200.compress_frame(data, 4, True, True, True), b200.compress_frame(data, 4, True, True, True, hc_level=level)
+            assert len(f_hc) <= len(f_fast), (n, level)
+            assert port.frame_decompress(f_hc, n + 8) == (n, data), (n, level)
+            if ref is not None:
+                assert ref.frame_decompress(f_hc, n + 8) == (n, data), ("LZ4F_decompress", n, level)
+            assert b200.decompress_frames(f_hc, n + 8) == data
+            b_fast, b_hc = b200.compress_lz4block(data, 1 << 16), b200.compress_lz4block(data, 1 << 16, hc_level=level)
+            assert len(b_hc) <= len(b_fast), (n, level)
+            assert port.lz4block_decompress(b_hc, n) == (n, data), (n, level)
+            assert b200.decompress_lz4block(b_hc, n) == data
+    noise = random.Random(3).randbytes(70000)                       # does not shrink: stored blocks either way
+    assert b200.compress_frame(noise, 4, hc_level=9) == b200.compress_frame(noise, 4)
+    assert b200.compress_lz4block(noise, 1 << 16, hc_level=9) == b200.compress_lz4block(noise, 1 << 16)
+
+
 def test_read_single_frame_and_expected_content_size(b200, port):
     """LZ4FrameIOStreamTest.java:310-426: a frame written with its content size reports it (getExpectedContentSize), one
     written without reports -1; with readSingleFrame the reader stops behind the first non-skippable frame -- four
