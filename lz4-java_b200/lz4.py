@@ -198,5 +198,13 @@ class LZ4Factory:
     def safeDecompressor(self) -> LZ4SafeDecompressor:
         return self._safe_dec
 
+    def unknownSizeDecompressor(self) -> LZ4SafeDecompressor:
+        """deprecated alias of safeDecompressor() (LZ4Factory.java:292-301)"""
+        return self._safe_dec
+
+    def decompressor(self) -> LZ4FastDecompressor:
+        """deprecated alias of fastDecompressor() (LZ4Factory.java:303-311)"""
+        return self._fast_dec
+
     def __str__(self):
         return "LZ4Factory:B200"
