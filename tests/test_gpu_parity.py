@@ -600,7 +600,7 @@ class _DevMem:
 
     def down(self, buf, dtype=np.uint8):
         if not self.sim:
-            self.torch.cuda.synchronize()
+            self.torch.cuda.synchronize(buf.device)
             buf = buf.cpu().numpy()
         return buf.view(np.uint8).reshape(-1).view(dtype)
 
