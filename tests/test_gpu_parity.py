@@ -627,9 +627,9 @@ def test_frames_written_with_flush(b200, port):
     """short blocks before the last one: the content checksum is folded across block boundaries that are not multiples
     of 16 on the device, the blocks are packed on the device, and a stream of tiny blocks asks for slots of its own size
     (not blockMaxSize each).  Against the restated reader (LZ4FrameInputStream.java:258-321)."""
-    rng = random.Random(77)
+    rng = random.Random(int(os.environ.get("B200_SEED", 77)))
     base = port.datagen(1 << 20, 0.5, 0.0, 9).tobytes()
-    for trial in range(4 if "sim" in os.environ.get("B200LZ4_TEST_SO", "") else 12):      # (the emulator build takes seconds per launch)
+    for trial in range(int(os.environ.get("B200_TRIALS", 4 if "sim" in os.environ.get("B200LZ4_TEST_SO", "") else 12))):   # (the emulator build takes seconds per launch)
         bs_code = rng.choice((4, 5, 6, 7))
         bs = 1 << (8 + 2 * bs_code)
         sizes = [rng.choice((1, 3, 5, 15, 16, 17, 31, 100, 4097, 65535, min(bs, 65536), min(bs, 200000))) for _ in range(rng.randrange(1, 40))]
