@@ -720,13 +720,30 @@ def run_b200(args):
             except Exception as e:          # noqa: BLE001
                 e2e_multi = {"error": str(e)[:300]}
         dist.barrier()
+    # None of these may take the headline down with it: a leg that fails (its own checks raise SystemExit) is reported as
+    # {"error": ...} under its key and the line is still printed.  The frame leg runs last: it is the only one with a second
+    # kernel polling the first, so if anything can leave the context unusable it is that one.
+    single = None
+    if rank == 0 and not args.no_secondary and not args.only:
+        try:
+            single = run_single_block(L, chk)
+        except (Exception, SystemExit) as e:        # noqa: BLE001
+            single = {"error": str(e)[:300]}
     secondary = {}
     if not args.no_secondary:
-        for key, fn in (("config5_xxh64", run_config5), ("config3_frame", run_config3), ("config4_hc9", run_config4)):
+        for key, fn in (("config5_xxh64", run_config5), ("config4_hc9", run_config4), ("config3_frame", run_config3)):
             if args.only and key.split("_")[0] not in args.only.split(","):
                 continue
-            secondary[key] = fn(args, L, chk, torch, dist, dev, rank, world, local, peak)
-    single = run_single_block(L, chk) if (rank == 0 and not args.no_secondary and not args.only) else None
+            try:
+                secondary[key] = fn(args, L, chk, torch, dist, dev, rank, world, local, peak)
+            except (Exception, SystemExit) as e:    # noqa: BLE001
+                secondary[key] = {"error": str(e)[:300]}
+                print(f"bench: {key} failed on rank {rank}: {e}", file=sys.stderr, flush=True)
+            if isinstance(secondary[key], dict) and "error" in secondary[key]:
+                try:
+                    torch.cuda.empty_cache()        # (the failed leg's buffers went with its frames)
+                except Exception:                   # noqa: BLE001
+                    pass
 
     if rank == 0:
         peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback)"
