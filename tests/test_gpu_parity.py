@@ -576,259 +576,6 @@ def test_frame_batch_decoder(b200, port):
     assert e.value.code == -9
 
 
-class _DevMem:
-    """device buffers for tests that call the C ABI with raw device pointers: torch CUDA tensors on a GPU box, plain
-    numpy arrays under the emulator build (its "device memory" is the host heap)"""
-
-    def __init__(self):
-        self.sim = "sim" in os.environ.get("B200LZ4_TEST_SO", "")
-        if not self.sim:
-            import torch
-            self.torch = torch
-
-    def up(self, arr, device=0):
-        arr = np.ascontiguousarray(arr)
-        if self.sim:
-            return arr.copy()
-        return self.torch.from_numpy(arr.view(np.uint8).reshape(-1)).to(self.torch.device("cuda", device))
-
-    def zeros(self, nbytes, device=0):
-        return self.up(np.zeros(max(nbytes, 16), dtype=np.uint8), device)
-
-    def ptr(self, buf):
-        return buf.ctypes.data if self.sim else buf.data_ptr()
-
-    def down(self, buf, dtype=np.uint8):
-        if not self.sim:
-            self.torch.cuda.synchronize(buf.device)
-            buf = buf.cpu().numpy()
-        return buf.view(np.uint8).reshape(-1).view(dtype)
-
-
-def _frame_of_pieces(port, pieces, bs_code, content_checksum=True, block_checksum=False, stored=()):
-    """an LZ4 frame whose blocks are exactly `pieces` (what LZ4FrameOutputStream writes when flush() is called between
-    writes, LZ4FrameOutputStream.java:204-251,268-277): short blocks anywhere, stored when they do not shrink or when asked"""
-    hdr = bytes([0x60 | (0x10 if block_checksum else 0) | (0x04 if content_checksum else 0), bs_code << 4])
-    out = bytearray(b"\x04\x22\x4d\x18" + hdr + bytes([(port.xxh32(hdr, 0) >> 8) & 0xFF]))
-    for i, piece in enumerate(pieces):
-        c = port.compress(piece)
-        raw = i in stored or len(c) >= len(piece)
-        payload = piece if raw else c
-        out += (len(payload) | (0x80000000 if raw else 0)).to_bytes(4, "little") + payload
-        if block_checksum:
-            out += port.xxh32(payload, 0).to_bytes(4, "little")
-    out += (0).to_bytes(4, "little")
-    if content_checksum:
-        out += port.xxh32(b"".join(pieces), 0).to_bytes(4, "little")
-    return bytes(out)
-
-
-def test_frames_written_with_flush(b200, port):
-    """short blocks before the last one: the content checksum is folded across block boundaries that are not multiples
-    of 16 on the device, the blocks are packed on the device, and a stream of tiny blocks asks for slots of its own size
-    (not blockMaxSize each).  Against the restated reader (LZ4FrameInputStream.java:258-321)."""
-    rng = random.Random(int(os.environ.get("B200_SEED", 77)))
-    base = port.datagen(1 << 20, 0.5, 0.0, 9).tobytes()
-    for trial in range(int(os.environ.get("B200_TRIALS", 4 if "sim" in os.environ.get("B200LZ4_TEST_SO", "") else 12))):   # (the emulator build takes seconds per launch)
-        bs_code = rng.choice((4, 5, 6, 7))
-        bs = 1 << (8 + 2 * bs_code)
-        sizes = [rng.choice((1, 3, 5, 15, 16, 17, 31, 100, 4097, 65535, min(bs, 65536), min(bs, 200000))) for _ in range(rng.randrange(1, 40))]
-        if trial == 0:
-            sizes = [5] * 300                                     # nothing but 5-byte stored blocks
-        if trial == 1:
-            sizes = [bs, 7, bs, bs, 1, 16, 33]
-        pieces = []
-        for n in sizes:
-            o = rng.randrange(0, len(base) - n) if n < len(base) else 0
-            pieces.append(rng.randbytes(n) if rng.random() < 0.2 else (base * (n // len(base) + 1))[o:o + n])
-        stored = {i for i in range(len(pieces)) if rng.random() < 0.15}
-        f = _frame_of_pieces(port, pieces, bs_code, content_checksum=trial % 3 != 2, block_checksum=bool(trial & 1), stored=stored)
-        want = b"".join(pieces)
-        r, out = port.frame_decompress(f, len(want) + 8)
-        assert r == len(want) and out == want, trial                # the builder writes what the restated reader accepts
-        assert b200.decompress_frames(f, len(want) + 8) == want, (trial, sizes)
-        both = f + port.frame_compress(base[:70000], 4, 1) + f       # gapped and contiguous frames in one call
-        assert b200.decompress_frames(both, 2 * len(want) + 70000) == want + base[:70000] + want, trial
-        if trial % 3 != 2 and want:
-            bad = bytearray(f); bad[-1] ^= 0x40                      # content checksum of a gapped frame
-            with pytest.raises(b200.LZ4FrameError) as e:
-                b200.decompress_frames(bytes(bad), len(want) + 8)
-            assert e.value.code == -7, trial
-        if want:
-            with pytest.raises(b200.LZ4FrameError) as e:
-                b200.decompress_frames(f, len(want) - 1)
-            assert e.value.code == -9
-    # slots: 300 five-byte stored blocks in a 4 MiB-block frame need kilobytes, not 300 x 4 MiB
-    import ctypes
-    from importlib import import_module
-    N = import_module(b200.__name__ + "._native")
-    f = np.frombuffer(_frame_of_pieces(port, [b"12345"] * 300, 7, stored=set(range(300))), dtype=np.uint8)
-    slot, err = ctypes.c_uint64(0), ctypes.c_int(0)
-    ix = N.lib().b200lz4f_index_create(f.ctypes.data, len(f), ctypes.byref(slot), ctypes.byref(err))
-    assert ix and err.value == 0 and slot.value == 300 * 16, (err.value, slot.value)
-    offs = np.zeros(300, dtype=np.uint64)
-    N.lib().b200lz4f_index_block_offsets(ix, offs.ctypes.data)
-    assert (offs == np.arange(300, dtype=np.uint64) * 16).all()
-    N.lib().b200lz4f_index_free(ix)
-    # the device entry point on a gapped frame: every check passes, -11 says "read the blocks one by one", and the blocks are
-    # where b200lz4f_index_block_offsets says, block_len_out bytes each
-    pieces = [base[:65536], base[100:107], base[7:65543], b"", base[5:38], rng.randbytes(300)]
-    pieces = [p for p in pieces if p]
-    f = np.frombuffer(_frame_of_pieces(port, pieces, 4, content_checksum=True, block_checksum=True), dtype=np.uint8)
-    M = _DevMem()
-    ix = N.lib().b200lz4f_index_create(f.ctypes.data, len(f), ctypes.byref(slot), ctypes.byref(err))
-    assert ix and err.value == 0
-    nb = N.lib().b200lz4f_index_blocks(ix)
-    assert nb == len(pieces) and N.lib().b200lz4f_index_frames(ix) == 1
-    d_src, d_slots = M.up(np.concatenate([f, np.zeros(64, dtype=np.uint8)])), M.zeros(slot.value + 64)
-    foff, flen, blen = np.zeros(1, dtype=np.uint64), np.zeros(1, dtype=np.uint64), np.zeros(nb, dtype=np.int32)
-    rc = N.lib().b200lz4f_decode_dev(ix, M.ptr(d_src), M.ptr(d_slots), foff.ctypes.data, flen.ctypes.data, blen.ctypes.data, None)
-    assert rc == -11 and int(flen[0]) == sum(map(len, pieces)) and [int(x) for x in blen] == [len(p) for p in pieces]
-    offs = np.zeros(nb, dtype=np.uint64)
-    N.lib().b200lz4f_index_block_offsets(ix, offs.ctypes.data)
-    got = M.down(d_slots)
-    for o, p in zip(offs, pieces):
-        assert got[int(o):int(o) + len(p)].tobytes() == p
-    bad = f.copy(); bad[-1] ^= 1                                   # the content checksum is verified BEFORE -11 is returned
-    ix2 = N.lib().b200lz4f_index_create(bad.ctypes.data, len(bad), ctypes.byref(slot), ctypes.byref(err))
-    d_bad = M.up(np.concatenate([bad, np.zeros(64, dtype=np.uint8)]))
-    assert N.lib().b200lz4f_decode_dev(ix2, M.ptr(d_bad), M.ptr(d_slots), None, None, None, None) == -7
-    N.lib().b200lz4f_index_free(ix); N.lib().b200lz4f_index_free(ix2)
-
-
-def test_container_writers_with_the_high_compressor(b200, port):
-    """LZ4FrameOutputStream / LZ4BlockOutputStream take the compressor as an argument (LZ4FrameOutputStream.java:132-133,
-    LZ4BlockOutputStream.java:96,124); with highCompressor(level) the containers must still be read by the sequential readers
-    (restated, and the reference's LZ4F_decompress when it is there), and must not come out larger than with the fast one."""
-    from oracle import oracle as O
-    try:
-        ref = O.Ref()
-    except (FileNotFoundError, OSError):
-        ref = None
-    sim = "sim" in os.environ.get("B200LZ4_TEST_SO", "")
-    for n in ((1, 70000) if sim else (0, 1, 65536, 200000, 1500000)):
-        data = port.datagen(n, 0.5, 0.0, 5).tobytes()
-        for level in ((9,) if sim else (1, 9, 17)):
-            f_fast, f_hc = b200.compress_frame(data, 4, True, True, True), b200.compress_frame(data, 4, True, True, True, hc_level=level)
-            assert len(f_hc) <= len(f_fast), (n, level)
-            assert port.frame_decompress(f_hc, n + 8) == (n, data), (n, level)
-            if ref is not None:
-                assert ref.frame_decompress(f_hc, n + 8) == (n, data), ("LZ4F_decompress", n, level)
-            assert b200.decompress_frames(f_hc, n + 8) == data
-            b_fast, b_hc = b200.compress_lz4block(data, 1 << 16), b200.compress_lz4block(data, 1 << 16, hc_level=level)
-            assert len(b_hc) <= len(b_fast), (n, level)
-            assert port.lz4block_decompress(b_hc, n) == (n, data), (n, level)
-            assert b200.decompress_lz4block(b_hc, n) == data
-    noise = random.Random(3).randbytes(70000)                       # does not shrink: stored blocks either way
-    assert b200.compress_frame(noise, 4, hc_level=9) == b200.compress_frame(noise, 4)
-    assert b200.compress_lz4block(noise, 1 << 16, hc_level=9) == b200.compress_lz4block(noise, 1 << 16)
-
-
-def test_read_single_frame_and_expected_content_size(b200, port):
-    """LZ4FrameIOStreamTest.java:310-426: a frame written with its content size reports it (getExpectedContentSize), one
-    written without reports -1; with readSingleFrame the reader stops behind the first non-skippable frame -- four
-    concatenated copies yield one -- and says how far it read; what follows that frame is not even looked at."""
-    import ctypes
-    data = port.datagen(300000, 0.5, 0.0, 77).tobytes()
-    with_size = b200.compress_frame(data, 7, True, False, True)
-    without = b200.compress_frame(data, 7, True, False, False)
-    assert b200.expected_content_size(with_size) == len(data)                      # :326-329
-    assert b200.expected_content_size(port.frame_compress(data, 4, 5)) == len(data)
-    assert b200.expected_content_size(without) == -1                               # :348-351
-    assert b200.decompress_frames(with_size, len(data), read_single_frame=True) == data
-    four = without * 4                                                              # :379-420
-    assert b200.decompress_frames(four, 4 * len(data)) == data * 4
-    assert b200.decompress_frames(four, 4 * len(data), read_single_frame=True) == data
-    assert b200.expected_content_size(four) == -1
-    skip = bytes([0x5A, 0x2A, 0x4D, 0x18, 3, 0, 0, 0, 9, 9, 9])
-    lead = skip + skip + with_size + b"\x00garbage that is not a frame"
-    assert b200.decompress_frames(lead, len(data), read_single_frame=True) == data  # skippable frames do not count as "the" frame
-    assert b200.expected_content_size(lead) == len(data)
-    with pytest.raises(b200.LZ4FrameError) as e:
-        b200.decompress_frames(lead, len(data))                                     # ... the multi-frame reader trips over the rest
-    assert e.value.code == -2
-    L = b200._native.lib()
-    buf = np.frombuffer(lead, dtype=np.uint8); out = np.zeros(len(data), dtype=np.uint8); used = ctypes.c_size_t(0)
-    assert L.b200lz4f_decompress_host_single(buf.ctypes.data, len(buf), out.ctypes.data, len(out), ctypes.byref(used)) == len(data)
-    assert used.value == 2 * len(skip) + len(with_size) and out.tobytes() == data
-    assert b200.expected_content_size(skip) == -1                                   # only skippable frames: no frame, no error (:141-147)
-    assert b200.decompress_frames(skip, 10, read_single_frame=True) == b""
-    for bad, code in ((b"", -1), (skip + b"\x04\x22", -1), (b"\x04\x22\x4d\x18\x60", -1), (b"\x01\x02\x03\x04rest", -2),
-                      (with_size[:4] + bytes([with_size[4] ^ 0x80]) + with_size[5:], -10),
-                      (with_size[:7] + bytes([with_size[7] ^ 1]) + with_size[8:], -3)):      # a bit of the content size: descriptor hash
-        with pytest.raises(b200.LZ4FrameError) as e:
-            b200.expected_content_size(bad)
-        assert e.value.code == code, (bad[:12], e.value.code, code)
-
-
-def test_frame_errors_come_in_stream_order(b200, port):
-    """LZ4FrameInputStream is a stream: of several things wrong with a container it reports the FIRST one it meets
-    (descriptor hash, then block by block checksum and decode, then at the EndMark content checksum before content size,
-    LZ4FrameInputStream.java:208-216, 264-273, 298-311), and a container cut short or malformed further on still fails
-    on an earlier checksum first.  One to three random faults per container, against the restated sequential reader."""
-    rng = random.Random(2024)
-    base = port.datagen(1 << 18, 0.5, 0.0, 21).tobytes()
-    sim = "sim" in os.environ.get("B200LZ4_TEST_SO", "")
-    seen = {}
-    for trial in range(int(os.environ.get("B200_TRIALS", 60 if sim else 400))):
-        frames = []
-        for _ in range(rng.randrange(1, 4)):
-            pieces = [base[o:o + n] for o, n in ((rng.randrange(0, 100000), rng.choice((1, 40, 700, 5000, 65536))) for _ in range(rng.randrange(0, 5)))]
-            if rng.random() < 0.5:
-                body = b"".join(pieces)
-                frames.append(port.frame_compress(body, rng.choice((4, 5)), rng.randrange(8)))   # flags: content checksum, block checksums, content size
-            else:
-                frames.append(_frame_of_pieces(port, pieces, rng.choice((4, 5)), content_checksum=rng.random() < 0.7, block_checksum=rng.random() < 0.5,
-                                               stored={i for i in range(len(pieces)) if rng.random() < 0.2}))
-        blob = bytearray(b"".join(frames))
-        total = 1 << 20
-        for _ in range(rng.randrange(1, 4)):
-            kind = rng.randrange(4)
-            if kind == 0 and len(blob) > 8:
-                del blob[rng.randrange(len(blob) - 8, len(blob)):]                   # cut short near the end
-            elif kind == 1 and len(blob) > 1:
-                del blob[rng.randrange(1, len(blob)):]                               # cut short anywhere
-            elif blob:
-                i = rng.randrange(len(blob)); blob[i] ^= 1 << rng.randrange(8)       # one flipped bit
-        want, out = port.frame_decompress(bytes(blob), total)
-        if want >= 0:
-            assert b200.decompress_frames(bytes(blob), total) == out, trial
-            seen["ok"] = seen.get("ok", 0) + 1
-            continue
-        with pytest.raises(b200.LZ4FrameError) as e:
-            b200.decompress_frames(bytes(blob), total)
-        assert e.value.code == want, (trial, e.value.code, want, bytes(blob).hex() if len(blob) < 400 else len(blob))
-        seen[want] = seen.get(want, 0) + 1
-    assert len([k for k in seen if k != "ok"]) >= (4 if sim else 6), seen              # the sweep met most of the codes
-    # the same for lz4-java's own container (LZ4BlockInputStream.java:191-264): premature end vs "Stream is corrupted" vs our -9
-    seen = {}
-    for trial in range(int(os.environ.get("B200_TRIALS", 60 if sim else 400))):
-        body = b"".join(base[o:o + n] for o, n in ((rng.randrange(0, 100000), rng.choice((1, 40, 700, 5000, 70000))) for _ in range(rng.randrange(0, 4))))
-        if rng.random() < 0.2:
-            body += rng.randbytes(3000)                                              # a stored block
-        blob = bytearray(port.lz4block_compress(body, rng.choice((64, 4096, 65536))))
-        for _ in range(rng.randrange(1, 4)):
-            kind = rng.randrange(3)
-            if kind == 0 and len(blob) > 1:
-                del blob[rng.randrange(1, len(blob)):]
-            elif blob:
-                i = rng.randrange(len(blob)); blob[i] ^= 1 << rng.randrange(8)
-        stop = rng.random() < 0.7
-        cap = len(body) + rng.choice((0, 0, 8, -1000))
-        cap = max(cap, 0)
-        want, out = port.lz4block_decompress(bytes(blob), cap, stop)
-        if want >= 0:
-            assert b200.decompress_lz4block(bytes(blob), cap, stop_on_empty_block=stop) == out, trial
-            seen["ok"] = seen.get("ok", 0) + 1
-            continue
-        with pytest.raises((EOFError, IOError)) as e:
-            b200.decompress_lz4block(bytes(blob), cap, stop_on_empty_block=stop)
-        got = -1 if isinstance(e.value, EOFError) else (-2 if "corrupted" in str(e.value) else -9)
-        assert got == want, (trial, got, want, str(e.value))
-        seen[want] = seen.get(want, 0) + 1
-    assert len(seen) >= 3, seen
-
-
 def test_frame_writer_and_lz4java_containers(b200, port):
     """(f)-2..4: frames / LZ4Block streams / length-prefixed blocks WRITTEN on the GPU path are read by the CPU
     restatements (and by the reference's LZ4F_decompress when available), and vice versa"""
@@ -1366,6 +1113,260 @@ def test_error_offsets_beyond_a_million_are_decoder_errors(b200, checker):
     with pytest.raises(b200.LZ4Exception) as e:
         b200.LZ4Factory.b200Instance().safeDecompressor().decompress(bytes(c), 0, len(c), bytearray(len(d)), 0, len(d))
     assert "offset" in str(e.value)
+
+
+# ---- written after round 2's last visit to a GPU: these ran on the emulator build only so far, so they come last
+class _DevMem:
+    """device buffers for tests that call the C ABI with raw device pointers: torch CUDA tensors on a GPU box, plain
+    numpy arrays under the emulator build (its "device memory" is the host heap)"""
+
+    def __init__(self):
+        self.sim = "sim" in os.environ.get("B200LZ4_TEST_SO", "")
+        if not self.sim:
+            import torch
+            self.torch = torch
+
+    def up(self, arr, device=0):
+        arr = np.ascontiguousarray(arr)
+        if self.sim:
+            return arr.copy()
+        return self.torch.from_numpy(arr.view(np.uint8).reshape(-1)).to(self.torch.device("cuda", device))
+
+    def zeros(self, nbytes, device=0):
+        return self.up(np.zeros(max(nbytes, 16), dtype=np.uint8), device)
+
+    def ptr(self, buf):
+        return buf.ctypes.data if self.sim else buf.data_ptr()
+
+    def down(self, buf, dtype=np.uint8):
+        if not self.sim:
+            self.torch.cuda.synchronize(buf.device)
+            buf = buf.cpu().numpy()
+        return buf.view(np.uint8).reshape(-1).view(dtype)
+
+
+def _frame_of_pieces(port, pieces, bs_code, content_checksum=True, block_checksum=False, stored=()):
+    """an LZ4 frame whose blocks are exactly `pieces` (what LZ4FrameOutputStream writes when flush() is called between
+    writes, LZ4FrameOutputStream.java:204-251,268-277): short blocks anywhere, stored when they do not shrink or when asked"""
+    hdr = bytes([0x60 | (0x10 if block_checksum else 0) | (0x04 if content_checksum else 0), bs_code << 4])
+    out = bytearray(b"\x04\x22\x4d\x18" + hdr + bytes([(port.xxh32(hdr, 0) >> 8) & 0xFF]))
+    for i, piece in enumerate(pieces):
+        c = port.compress(piece)
+        raw = i in stored or len(c) >= len(piece)
+        payload = piece if raw else c
+        out += (len(payload) | (0x80000000 if raw else 0)).to_bytes(4, "little") + payload
+        if block_checksum:
+            out += port.xxh32(payload, 0).to_bytes(4, "little")
+    out += (0).to_bytes(4, "little")
+    if content_checksum:
+        out += port.xxh32(b"".join(pieces), 0).to_bytes(4, "little")
+    return bytes(out)
+
+
+def test_frames_written_with_flush(b200, port):
+    """short blocks before the last one: the content checksum is folded across block boundaries that are not multiples
+    of 16 on the device, the blocks are packed on the device, and a stream of tiny blocks asks for slots of its own size
+    (not blockMaxSize each).  Against the restated reader (LZ4FrameInputStream.java:258-321)."""
+    rng = random.Random(int(os.environ.get("B200_SEED", 77)))
+    base = port.datagen(1 << 20, 0.5, 0.0, 9).tobytes()
+    for trial in range(int(os.environ.get("B200_TRIALS", 4 if "sim" in os.environ.get("B200LZ4_TEST_SO", "") else 12))):   # (the emulator build takes seconds per launch)
+        bs_code = rng.choice((4, 5, 6, 7))
+        bs = 1 << (8 + 2 * bs_code)
+        sizes = [rng.choice((1, 3, 5, 15, 16, 17, 31, 100, 4097, 65535, min(bs, 65536), min(bs, 200000))) for _ in range(rng.randrange(1, 40))]
+        if trial == 0:
+            sizes = [5] * 300                                     # nothing but 5-byte stored blocks
+        if trial == 1:
+            sizes = [bs, 7, bs, bs, 1, 16, 33]
+        pieces = []
+        for n in sizes:
+            o = rng.randrange(0, len(base) - n) if n < len(base) else 0
+            pieces.append(rng.randbytes(n) if rng.random() < 0.2 else (base * (n // len(base) + 1))[o:o + n])
+        stored = {i for i in range(len(pieces)) if rng.random() < 0.15}
+        f = _frame_of_pieces(port, pieces, bs_code, content_checksum=trial % 3 != 2, block_checksum=bool(trial & 1), stored=stored)
+        want = b"".join(pieces)
+        r, out = port.frame_decompress(f, len(want) + 8)
+        assert r == len(want) and out == want, trial                # the builder writes what the restated reader accepts
+        assert b200.decompress_frames(f, len(want) + 8) == want, (trial, sizes)
+        both = f + port.frame_compress(base[:70000], 4, 1) + f       # gapped and contiguous frames in one call
+        assert b200.decompress_frames(both, 2 * len(want) + 70000) == want + base[:70000] + want, trial
+        if trial % 3 != 2 and want:
+            bad = bytearray(f); bad[-1] ^= 0x40                      # content checksum of a gapped frame
+            with pytest.raises(b200.LZ4FrameError) as e:
+                b200.decompress_frames(bytes(bad), len(want) + 8)
+            assert e.value.code == -7, trial
+        if want:
+            with pytest.raises(b200.LZ4FrameError) as e:
+                b200.decompress_frames(f, len(want) - 1)
+            assert e.value.code == -9
+    # slots: 300 five-byte stored blocks in a 4 MiB-block frame need kilobytes, not 300 x 4 MiB
+    import ctypes
+    from importlib import import_module
+    N = import_module(b200.__name__ + "._native")
+    f = np.frombuffer(_frame_of_pieces(port, [b"12345"] * 300, 7, stored=set(range(300))), dtype=np.uint8)
+    slot, err = ctypes.c_uint64(0), ctypes.c_int(0)
+    ix = N.lib().b200lz4f_index_create(f.ctypes.data, len(f), ctypes.byref(slot), ctypes.byref(err))
+    assert ix and err.value == 0 and slot.value == 300 * 16, (err.value, slot.value)
+    offs = np.zeros(300, dtype=np.uint64)
+    N.lib().b200lz4f_index_block_offsets(ix, offs.ctypes.data)
+    assert (offs == np.arange(300, dtype=np.uint64) * 16).all()
+    N.lib().b200lz4f_index_free(ix)
+    # the device entry point on a gapped frame: every check passes, -11 says "read the blocks one by one", and the blocks are
+    # where b200lz4f_index_block_offsets says, block_len_out bytes each
+    pieces = [base[:65536], base[100:107], base[7:65543], b"", base[5:38], rng.randbytes(300)]
+    pieces = [p for p in pieces if p]
+    f = np.frombuffer(_frame_of_pieces(port, pieces, 4, content_checksum=True, block_checksum=True), dtype=np.uint8)
+    M = _DevMem()
+    ix = N.lib().b200lz4f_index_create(f.ctypes.data, len(f), ctypes.byref(slot), ctypes.byref(err))
+    assert ix and err.value == 0
+    nb = N.lib().b200lz4f_index_blocks(ix)
+    assert nb == len(pieces) and N.lib().b200lz4f_index_frames(ix) == 1
+    d_src, d_slots = M.up(np.concatenate([f, np.zeros(64, dtype=np.uint8)])), M.zeros(slot.value + 64)
+    foff, flen, blen = np.zeros(1, dtype=np.uint64), np.zeros(1, dtype=np.uint64), np.zeros(nb, dtype=np.int32)
+    rc = N.lib().b200lz4f_decode_dev(ix, M.ptr(d_src), M.ptr(d_slots), foff.ctypes.data, flen.ctypes.data, blen.ctypes.data, None)
+    assert rc == -11 and int(flen[0]) == sum(map(len, pieces)) and [int(x) for x in blen] == [len(p) for p in pieces]
+    offs = np.zeros(nb, dtype=np.uint64)
+    N.lib().b200lz4f_index_block_offsets(ix, offs.ctypes.data)
+    got = M.down(d_slots)
+    for o, p in zip(offs, pieces):
+        assert got[int(o):int(o) + len(p)].tobytes() == p
+    bad = f.copy(); bad[-1] ^= 1                                   # the content checksum is verified BEFORE -11 is returned
+    ix2 = N.lib().b200lz4f_index_create(bad.ctypes.data, len(bad), ctypes.byref(slot), ctypes.byref(err))
+    d_bad = M.up(np.concatenate([bad, np.zeros(64, dtype=np.uint8)]))
+    assert N.lib().b200lz4f_decode_dev(ix2, M.ptr(d_bad), M.ptr(d_slots), None, None, None, None) == -7
+    N.lib().b200lz4f_index_free(ix); N.lib().b200lz4f_index_free(ix2)
+
+
+def test_container_writers_with_the_high_compressor(b200, port):
+    """LZ4FrameOutputStream / LZ4BlockOutputStream take the compressor as an argument (LZ4FrameOutputStream.java:132-133,
+    LZ4BlockOutputStream.java:96,124); with highCompressor(level) the containers must still be read by the sequential readers
+    (restated, and the reference's LZ4F_decompress when it is there), and must not come out larger than with the fast one."""
+    from oracle import oracle as O
+    try:
+        ref = O.Ref()
+    except (FileNotFoundError, OSError):
+        ref = None
+    sim = "sim" in os.environ.get("B200LZ4_TEST_SO", "")
+    for n in ((1, 70000) if sim else (0, 1, 65536, 200000, 1500000)):
+        data = port.datagen(n, 0.5, 0.0, 5).tobytes()
+        for level in ((9,) if sim else (1, 9, 17)):
+            f_fast, f_hc = b200.compress_frame(data, 4, True, True, True), b200.compress_frame(data, 4, True, True, True, hc_level=level)
+            assert len(f_hc) <= len(f_fast), (n, level)
+            assert port.frame_decompress(f_hc, n + 8) == (n, data), (n, level)
+            if ref is not None:
+                assert ref.frame_decompress(f_hc, n + 8) == (n, data), ("LZ4F_decompress", n, level)
+            assert b200.decompress_frames(f_hc, n + 8) == data
+            b_fast, b_hc = b200.compress_lz4block(data, 1 << 16), b200.compress_lz4block(data, 1 << 16, hc_level=level)
+            assert len(b_hc) <= len(b_fast), (n, level)
+            assert port.lz4block_decompress(b_hc, n) == (n, data), (n, level)
+            assert b200.decompress_lz4block(b_hc, n) == data
+    noise = random.Random(3).randbytes(70000)                       # does not shrink: stored blocks either way
+    assert b200.compress_frame(noise, 4, hc_level=9) == b200.compress_frame(noise, 4)
+    assert b200.compress_lz4block(noise, 1 << 16, hc_level=9) == b200.compress_lz4block(noise, 1 << 16)
+
+
+def test_read_single_frame_and_expected_content_size(b200, port):
+    """LZ4FrameIOStreamTest.java:310-426: a frame written with its content size reports it (getExpectedContentSize), one
+    written without reports -1; with readSingleFrame the reader stops behind the first non-skippable frame -- four
+    concatenated copies yield one -- and says how far it read; what follows that frame is not even looked at."""
+    import ctypes
+    data = port.datagen(300000, 0.5, 0.0, 77).tobytes()
+    with_size = b200.compress_frame(data, 7, True, False, True)
+    without = b200.compress_frame(data, 7, True, False, False)
+    assert b200.expected_content_size(with_size) == len(data)                      # :326-329
+    assert b200.expected_content_size(port.frame_compress(data, 4, 5)) == len(data)
+    assert b200.expected_content_size(without) == -1                               # :348-351
+    assert b200.decompress_frames(with_size, len(data), read_single_frame=True) == data
+    four = without * 4                                                              # :379-420
+    assert b200.decompress_frames(four, 4 * len(data)) == data * 4
+    assert b200.decompress_frames(four, 4 * len(data), read_single_frame=True) == data
+    assert b200.expected_content_size(four) == -1
+    skip = bytes([0x5A, 0x2A, 0x4D, 0x18, 3, 0, 0, 0, 9, 9, 9])
+    lead = skip + skip + with_size + b"\x00garbage that is not a frame"
+    assert b200.decompress_frames(lead, len(data), read_single_frame=True) == data  # skippable frames do not count as "the" frame
+    assert b200.expected_content_size(lead) == len(data)
+    with pytest.raises(b200.LZ4FrameError) as e:
+        b200.decompress_frames(lead, len(data))                                     # ... the multi-frame reader trips over the rest
+    assert e.value.code == -2
+    L = b200._native.lib()
+    buf = np.frombuffer(lead, dtype=np.uint8); out = np.zeros(len(data), dtype=np.uint8); used = ctypes.c_size_t(0)
+    assert L.b200lz4f_decompress_host_single(buf.ctypes.data, len(buf), out.ctypes.data, len(out), ctypes.byref(used)) == len(data)
+    assert used.value == 2 * len(skip) + len(with_size) and out.tobytes() == data
+    assert b200.expected_content_size(skip) == -1                                   # only skippable frames: no frame, no error (:141-147)
+    assert b200.decompress_frames(skip, 10, read_single_frame=True) == b""
+    for bad, code in ((b"", -1), (skip + b"\x04\x22", -1), (b"\x04\x22\x4d\x18\x60", -1), (b"\x01\x02\x03\x04rest", -2),
+                      (with_size[:4] + bytes([with_size[4] ^ 0x80]) + with_size[5:], -10),
+                      (with_size[:7] + bytes([with_size[7] ^ 1]) + with_size[8:], -3)):      # a bit of the content size: descriptor hash
+        with pytest.raises(b200.LZ4FrameError) as e:
+            b200.expected_content_size(bad)
+        assert e.value.code == code, (bad[:12], e.value.code, code)
+
+
+def test_frame_errors_come_in_stream_order(b200, port):
+    """LZ4FrameInputStream is a stream: of several things wrong with a container it reports the FIRST one it meets
+    (descriptor hash, then block by block checksum and decode, then at the EndMark content checksum before content size,
+    LZ4FrameInputStream.java:208-216, 264-273, 298-311), and a container cut short or malformed further on still fails
+    on an earlier checksum first.  One to three random faults per container, against the restated sequential reader."""
+    rng = random.Random(2024)
+    base = port.datagen(1 << 18, 0.5, 0.0, 21).tobytes()
+    sim = "sim" in os.environ.get("B200LZ4_TEST_SO", "")
+    seen = {}
+    for trial in range(int(os.environ.get("B200_TRIALS", 60 if sim else 400))):
+        frames = []
+        for _ in range(rng.randrange(1, 4)):
+            pieces = [base[o:o + n] for o, n in ((rng.randrange(0, 100000), rng.choice((1, 40, 700, 5000, 65536))) for _ in range(rng.randrange(0, 5)))]
+            if rng.random() < 0.5:
+                body = b"".join(pieces)
+                frames.append(port.frame_compress(body, rng.choice((4, 5)), rng.randrange(8)))   # flags: content checksum, block checksums, content size
+            else:
+                frames.append(_frame_of_pieces(port, pieces, rng.choice((4, 5)), content_checksum=rng.random() < 0.7, block_checksum=rng.random() < 0.5,
+                                               stored={i for i in range(len(pieces)) if rng.random() < 0.2}))
+        blob = bytearray(b"".join(frames))
+        total = 1 << 20
+        for _ in range(rng.randrange(1, 4)):
+            kind = rng.randrange(4)
+            if kind == 0 and len(blob) > 8:
+                del blob[rng.randrange(len(blob) - 8, len(blob)):]                   # cut short near the end
+            elif kind == 1 and len(blob) > 1:
+                del blob[rng.randrange(1, len(blob)):]                               # cut short anywhere
+            elif blob:
+                i = rng.randrange(len(blob)); blob[i] ^= 1 << rng.randrange(8)       # one flipped bit
+        want, out = port.frame_decompress(bytes(blob), total)
+        if want >= 0:
+            assert b200.decompress_frames(bytes(blob), total) == out, trial
+            seen["ok"] = seen.get("ok", 0) + 1
+            continue
+        with pytest.raises(b200.LZ4FrameError) as e:
+            b200.decompress_frames(bytes(blob), total)
+        assert e.value.code == want, (trial, e.value.code, want, bytes(blob).hex() if len(blob) < 400 else len(blob))
+        seen[want] = seen.get(want, 0) + 1
+    assert len([k for k in seen if k != "ok"]) >= (4 if sim else 6), seen              # the sweep met most of the codes
+    # the same for lz4-java's own container (LZ4BlockInputStream.java:191-264): premature end vs "Stream is corrupted" vs our -9
+    seen = {}
+    for trial in range(int(os.environ.get("B200_TRIALS", 60 if sim else 400))):
+        body = b"".join(base[o:o + n] for o, n in ((rng.randrange(0, 100000), rng.choice((1, 40, 700, 5000, 70000))) for _ in range(rng.randrange(0, 4))))
+        if rng.random() < 0.2:
+            body += rng.randbytes(3000)                                              # a stored block
+        blob = bytearray(port.lz4block_compress(body, rng.choice((64, 4096, 65536))))
+        for _ in range(rng.randrange(1, 4)):
+            kind = rng.randrange(3)
+            if kind == 0 and len(blob) > 1:
+                del blob[rng.randrange(1, len(blob)):]
+            elif blob:
+                i = rng.randrange(len(blob)); blob[i] ^= 1 << rng.randrange(8)
+        stop = rng.random() < 0.7
+        cap = len(body) + rng.choice((0, 0, 8, -1000))
+        cap = max(cap, 0)
+        want, out = port.lz4block_decompress(bytes(blob), cap, stop)
+        if want >= 0:
+            assert b200.decompress_lz4block(bytes(blob), cap, stop_on_empty_block=stop) == out, trial
+            seen["ok"] = seen.get("ok", 0) + 1
+            continue
+        with pytest.raises((EOFError, IOError)) as e:
+            b200.decompress_lz4block(bytes(blob), cap, stop_on_empty_block=stop)
+        got = -1 if isinstance(e.value, EOFError) else (-2 if "corrupted" in str(e.value) else -9)
+        assert got == want, (trial, got, want, str(e.value))
+        seen[want] = seen.get(want, 0) + 1
+    assert len(seen) >= 3, seen
 
 
 def test_device_side_compaction_and_stitch(b200, checker):
