@@ -386,8 +386,9 @@ lz4_compress_wide_kernel(const uint8_t* __restrict__ src_base, const uint64_t* _
                 nq = search(q + fl);
             }
             // the next sequence's two loads go out before this one is booked: their latency is the chain's critical path
-            uint32_t ncode = 0, ndist = 0;
-            if (nq < uint32_t(CH)) { ncode = fls[nq]; ndist = ds[nq]; }
+            // (unconditionally: nq is at most 62 entries past the chunk, still inside this CTA's shared memory, and a value
+            // read there is never used -- the loop ends)
+            const uint32_t ncode = fls[nq], ndist = ds[nq];
             if (lane == 0) s_rec[k] = make_uint2(ms | (dist << 16), fl);
             ip = int(ms + fl);
             q = nq; code = ncode; dist = ndist;
